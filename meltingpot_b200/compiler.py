@@ -1,0 +1,755 @@
+"""Substrate compiler: reference lab2d settings dict -> flat numeric tables (MPB blob).
+
+Replaces, for the hot path only, what the reference does at build time:
+  * `builder.builder` (`/root/reference/meltingpot/utils/substrates/builder.py:142-192`)
+    flattens the settings for Lua; we flatten them into tables instead.
+  * `BaseSimulation.__init__` / `prefab_utils.buildGameObjectConfigs` walk the ASCII
+    map row-major and instantiate prefabs
+    (`/root/reference/meltingpot/lua/modules/base_simulation.lua:102-134`,
+    `prefab_utils.lua:92-109,163-176`): object creation order = scene, configured
+    game objects (avatars), then map objects row-major.
+  * `BaseSimulation:worldConfig` (`base_simulation.lua:253-320`) builds layers
+    (render order), states, hits; `_addShapesToTileSet`
+    (`component_library.lua:567-597`) builds sprites.
+
+The compiler CONSUMES the reference configs as data (imported from a reference
+checkout when available); compiled blobs for the supported substrates are
+committed under `meltingpot_b200/data/` because the reference tree is not
+present on the GPU box.
+"""
+
+from __future__ import annotations
+
+import copy
+import json
+import os
+import sys
+import types
+from typing import Any, Dict, List, Mapping, Optional, Sequence
+
+import numpy as np
+
+from meltingpot_b200 import blob as blob_lib
+
+# ---------------------------------------------------------------------------
+# Enumerations mirrored from include/mpb_format.h
+# ---------------------------------------------------------------------------
+META = dict(FAMILY=0, W=1, H=2, L=3, P=4, SPRITE_SIZE=5, TOPOLOGY=6,
+            MAX_FRAMES=7, N_OBJECTS=8, N_KINDS=9, N_STATES=10, N_COMPS=11,
+            N_SPRITES=12, N_HITS=13, N_GROUPS=14, VIEW_LEFT=15, VIEW_RIGHT=16,
+            VIEW_FORWARD=17, VIEW_BACKWARD=18, N_ACTIONS=19,
+            N_ACTION_FIELDS=20, OOB_SPRITE=21, OOV_SPRITE=22, N_SCALAR_OBS=23)
+META_COUNT = 32
+FAMILY = {'clean_up': 1, 'commons_harvest': 2, 'territory': 3}
+COMP = dict(StateManager=1, Transform=2, Appearance=3, BeamBlocker=4, Edible=5,
+            AppleGrow=6, DirtTracker=7, DirtCleaning=8, Avatar=9, Zapper=10,
+            ReadyToShootObservation=11, Cleaner=12, Taste=13,
+            AllNonselfCumulants=14, AvatarMetricReporter=15, RiverMonitor=16,
+            DirtSpawner=17, StochasticIntervalEpisodeEnding=18, GlobalData=19,
+            Animation=20, AdditionalSprites=21, Neighborhoods=22,
+            DensityRegrow=23, LocationObserver=24)
+COMP_NI, COMP_ND = 12, 6
+ACTION_FIELDS = {'move': 0, 'turn': 1, 'fireZap': 2, 'fireClean': 3,
+                 'fireClaim': 3}
+SCALAR_OBS = {'READY_TO_SHOOT': 0, 'NUM_OTHERS_WHO_CLEANED_THIS_STEP': 1}
+COMPASS = {'N': 0, 'E': 1, 'S': 2, 'W': 3}
+BASE_LAYERS = ['logic', 'alternateLogic', 'background', 'lowerPhysical',
+               'upperPhysical', 'overlay', 'superOverlay']
+_TASTE_ROLES = {'free': 0, 'cleaner': 1, 'consumer': 2}
+_HIT_OF = {'Zapper': ('zapHit', 'beamZap', 'BeamZap'),
+           'Cleaner': ('cleanHit', 'beamClean', 'BeamClean')}
+
+
+# ---------------------------------------------------------------------------
+# Loading reference configs without executing meltingpot/__init__.py
+# ---------------------------------------------------------------------------
+def _stub_package(name: str, path: str) -> None:
+  if name not in sys.modules:
+    module = types.ModuleType(name)
+    module.__path__ = [path]
+    sys.modules[name] = module
+
+
+def reference_root() -> Optional[str]:
+  for cand in (os.environ.get('MELTINGPOT_REFERENCE_ROOT'), '/root/reference'):
+    if cand and os.path.isdir(os.path.join(cand, 'meltingpot', 'configs')):
+      return cand
+  return None
+
+
+def load_reference_config(name: str, root: Optional[str] = None):
+  """Imports `meltingpot.configs.substrates.<name>` from a reference checkout.
+
+  The package `__init__` pulls in dmlab2d/chex/reactivex which are absent here,
+  so namespace stubs are registered for the parent packages instead
+  (`/root/reference/meltingpot/__init__.py:18`).
+  """
+  from meltingpot_b200 import shims  # pylint: disable=g-import-not-at-top
+  shims.install()
+  root = root or reference_root()
+  if root is None:
+    raise FileNotFoundError('no Melting Pot reference checkout found; set '
+                            'MELTINGPOT_REFERENCE_ROOT')
+  base = os.path.join(root, 'meltingpot')
+  _stub_package('meltingpot', base)
+  _stub_package('meltingpot.utils', os.path.join(base, 'utils'))
+  _stub_package('meltingpot.utils.substrates',
+                os.path.join(base, 'utils', 'substrates'))
+  _stub_package('meltingpot.configs', os.path.join(base, 'configs'))
+  import importlib  # pylint: disable=g-import-not-at-top
+  configs = importlib.import_module('meltingpot.configs.substrates')
+  return configs.get_config(name)
+
+
+def _plain(value: Any) -> Any:
+  """ConfigDict / tuples -> plain dict / list, recursively."""
+  if hasattr(value, 'to_dict') and not isinstance(value, dict):
+    value = value.to_dict()
+  if isinstance(value, Mapping):
+    return {k: _plain(v) for k, v in value.items()}
+  if isinstance(value, (list, tuple)):
+    return [_plain(v) for v in value]
+  return value
+
+
+# ---------------------------------------------------------------------------
+# Sprites
+# ---------------------------------------------------------------------------
+def _rgba(color: Sequence[int]) -> List[int]:
+  color = [int(c) for c in color]
+  if len(color) == 3:
+    color.append(255)
+  return color
+
+
+def text_to_image(text: str, palette: Mapping[str, Sequence[int]]) -> np.ndarray:
+  """ASCII shape + palette -> uint8 [h, w, 4] (component_library.lua:567-597)."""
+  rows = [r for r in text.strip('\n').split('\n')]
+  h, w = len(rows), len(rows[0])
+  img = np.zeros((h, w, 4), np.uint8)
+  for y, row in enumerate(rows):
+    if len(row) != w:
+      raise ValueError('ragged sprite text')
+    for x, ch in enumerate(row):
+      if ch not in palette:
+        raise KeyError(f'palette has no entry for {ch!r}')
+      img[y, x] = _rgba(palette[ch])
+  return img
+
+
+def downscale_box(img: np.ndarray, size: int) -> np.ndarray:
+  """Integer box average with round-half-up (policy A.15; parity unpinned)."""
+  h, w, _ = img.shape
+  if h == size and w == size:
+    return img
+  if h % size or w % size:
+    raise ValueError(f'cannot box-scale {h}x{w} to {size}')
+  fy, fx = h // size, w // size
+  acc = img.astype(np.uint32).reshape(size, fy, size, fx, 4).sum(axis=(1, 3))
+  n = fy * fx
+  return ((acc * 2 + n) // (2 * n)).astype(np.uint8)
+
+
+def four_facings(img: np.ndarray, no_rotate: bool) -> np.ndarray:
+  """[4, s, s, 4]: facing N, E, S, W. Rotating sprites turn clockwise (A.12)."""
+  if no_rotate:
+    return np.stack([img] * 4)
+  return np.stack([np.rot90(img, k=-k) for k in range(4)])
+
+
+class SpriteSet:
+  """Name -> [4, s, s, 4] images, in first-registration order."""
+
+  def __init__(self, size: int):
+    self.size = size
+    self.names: List[str] = []
+    self.images: Dict[str, np.ndarray] = {}
+
+  def _ensure(self, name: str) -> None:
+    if name not in self.images:
+      self.names.append(name)
+      self.images[name] = np.zeros((4, self.size, self.size, 4), np.uint8)
+
+  def add_color(self, name: str, color: Sequence[int]) -> None:
+    self._ensure(name)
+    self.images[name][:] = np.array(_rgba(color), np.uint8)
+
+  def add_shape(self, name: str, text, palette, no_rotate: bool) -> None:
+    if isinstance(text, (list, tuple)) and len(text) == 4:
+      if not no_rotate:
+        raise ValueError('explicit 4-facing sprites need noRotate=True')
+      self._ensure(name)
+      for k in range(4):
+        img = downscale_box(text_to_image(text[k], palette), self.size)
+        self.images[name][k] = img
+      return
+    img = downscale_box(text_to_image(text, palette), self.size)
+    self._ensure(name)
+    self.images[name][:] = four_facings(img, bool(no_rotate))
+
+  def add_from_appearance(self, kw: Mapping[str, Any], prefix: str = 'sprite'):
+    mode = kw.get('renderMode', 'colored_square')
+    names = kw.get(prefix + 'Names', [])
+    key = lambda s: ('custom' + s[0].upper() + s[1:]) if prefix == 'customSprite' else s
+    if prefix == 'customSprite':
+      colors = kw.get('customSpriteRGBColors', [])
+      shapes = kw.get('customSpriteShapes', [])
+      palettes = kw.get('customPalettes', [])
+      no_rot = kw.get('customNoRotates', [])
+    else:
+      colors = kw.get('spriteRGBColors', [])
+      shapes = kw.get('spriteShapes', [])
+      palettes = kw.get('palettes', [])
+      no_rot = kw.get('noRotates', [])
+    del key
+    for i, name in enumerate(names):
+      if mode == 'colored_square':
+        self.add_color(name, colors[i])
+      elif mode == 'ascii_shape':
+        self.add_shape(name, shapes[i], palettes[i],
+                       bool(no_rot[i]) if i < len(no_rot) else False)
+      elif mode == 'invisible':
+        pass
+      else:
+        raise ValueError(mode)
+
+  def index(self, name: str) -> int:
+    return self.names.index(name)
+
+  def atlas(self) -> np.ndarray:
+    return np.stack([self.images[n] for n in self.names])
+
+
+# ---------------------------------------------------------------------------
+# World model
+# ---------------------------------------------------------------------------
+def _first(components, name):
+  for c in components:
+    if c['component'] == name:
+      return c
+  return None
+
+
+def _map_rows(ascii_map: str) -> List[str]:
+  # prefab_utils.lua:92-109 strips leading newlines only; a trailing newline
+  # terminates the last row.
+  text = ascii_map.lstrip('\n')
+  rows = text.split('\n')
+  while rows and rows[-1] == '':
+    rows.pop()
+  return rows
+
+
+def _expand_prefab(spec, prefabs, out, x, y):
+  if isinstance(spec, Mapping):
+    if spec['type'] == 'all':
+      for p in spec['list']:
+        _expand_prefab(p, prefabs, out, x, y)
+    else:
+      raise NotImplementedError(
+          f"charPrefabMap type {spec['type']!r} (random choice at build time) "
+          'is not supported by the B200 engine')
+  else:
+    if spec not in prefabs:
+      raise KeyError(f"Prefab with name '{spec}' not found in prefabs.")
+    out.append((prefabs[spec], x, y))
+
+
+class WorldModel:
+  """Everything the engines need, as python lists prior to packing."""
+
+  def __init__(self, settings: Mapping[str, Any]):
+    s = _plain(settings)
+    sim = s['simulation']
+    self.level = s['levelName']
+    fam = self.level
+    for key in FAMILY:
+      if fam.startswith(key):
+        fam = key
+    if fam not in FAMILY:
+      raise NotImplementedError(f'substrate family {self.level!r} is not '
+                                'supported by the B200 engine')
+    self.family = fam
+    self.num_players = int(s['numPlayers'])
+    self.sprite_size = int(s.get('spriteSize', 8))
+    self.topology = {'BOUNDED': 0, 'TORUS': 1}[s.get('topology', 'BOUNDED')]
+    self.max_frames = int(s.get('maxEpisodeLengthFrames', 3600))
+    rows = _map_rows(sim['map'])
+    self.H, self.W = len(rows), max(len(r) for r in rows)
+
+    # ---- objects in creation order (base_simulation.lua:102-134) ----------
+    objs = []  # (config, x, y)
+    if sim.get('scene') is not None:
+      objs.append((sim['scene'], 0, 0))
+    for go in sim.get('gameObjects', []):
+      objs.append((go, 0, 0))
+    cpm = {str(k): v for k, v in sim['charPrefabMap'].items()}
+    for y, row in enumerate(rows):
+      for x, ch in enumerate(row):
+        if ch in cpm:
+          _expand_prefab(cpm[ch], sim['prefabs'], objs, x, y)
+    self.objects_cfg = objs
+
+    # ---- layers, hits (base_simulation.lua:263-271; addHits) ---------------
+    self.layers = list(BASE_LAYERS)
+    if self.family == 'territory':
+      # lua/levels/territory/init.lua:30-37 appends two render layers.
+      self.layers += ['directionIndicatorLayer', 'superDirectionIndicatorLayer']
+    self.hits: List[tuple] = []  # (name, layer, sprite)
+    for cfg, _, _ in objs:
+      for c in cfg['components']:
+        if c['component'] in _HIT_OF:
+          hit, layer, sprite = _HIT_OF[c['component']]
+          if hit not in [h[0] for h in self.hits]:
+            self.hits.append((hit, layer, sprite))
+          if layer not in self.layers:
+            self.layers.append(layer)
+
+    # ---- sprites (base_simulation.lua:322-329) -----------------------------
+    sp = SpriteSet(self.sprite_size)
+    sp.add_color('OutOfBounds', (0, 0, 0))
+    sp.add_color('OutOfView', (80, 80, 80))
+    for cfg, _, _ in objs:
+      for c in cfg['components']:
+        kw = c.get('kwargs', {}) or {}
+        if c['component'] == 'Appearance':
+          sp.add_from_appearance(kw)
+        elif c['component'] == 'AdditionalSprites':
+          sp.add_from_appearance(kw, prefix='customSprite')
+        elif c['component'] == 'Zapper':
+          sp.add_color('BeamZap', kw.get('beamColor', (252, 252, 106)))
+        elif c['component'] == 'Cleaner':
+          sp.add_color('BeamClean', (99, 223, 242, 175))
+    self.sprites = sp
+
+    # ---- groups -------------------------------------------------------------
+    self.groups: List[str] = []
+    for cfg, _, _ in objs:
+      sm = _first(cfg['components'], 'StateManager')
+      for st in sm['kwargs']['stateConfigs']:
+        for g in st.get('groups', []) or []:
+          if g not in self.groups:
+            self.groups.append(g)
+    if len(self.groups) > 31:
+      raise ValueError('too many groups')
+
+    # ---- kinds / states / comps / objects ----------------------------------
+    self.kinds: List[List[int]] = []
+    self.states: List[List[int]] = []
+    self.comps_i: List[List[int]] = []
+    self.comps_d: List[List[float]] = []
+    self.objects: List[List[int]] = []
+    self.kind_names: List[str] = []
+    self.state_names: List[List[str]] = []
+    kind_of: Dict[str, int] = {}
+    self.avatar_objs: List[int] = []
+    self.view = None
+    self.sprite_maps: Dict[int, Dict[str, str]] = {}
+    for oid, (cfg, x, y) in enumerate(objs):
+      comps = cfg['components']
+      tr = _first(comps, 'Transform')
+      tkw = (tr or {}).get('kwargs', {}) or {}
+      orient = COMPASS[tkw.get('orientation', 'N')]
+      if 'position' in tkw and tkw['position'] not in ([0, 0], None):
+        x, y = tkw['position']
+      stripped = copy.deepcopy(comps)
+      for c in stripped:
+        if c['component'] == 'Transform':
+          c.pop('kwargs', None)
+      key = json.dumps([cfg.get('name', ''), stripped], sort_keys=True,
+                       default=str)
+      if key not in kind_of:
+        kind_of[key] = self._add_kind(cfg)
+      kid = kind_of[key]
+      sm = _first(comps, 'StateManager')['kwargs']
+      init = self.state_names[kid].index(sm['initialState'])
+      self.objects.append([kid, int(x), int(y), orient, init])
+      if self.kinds[kid][4]:
+        self.avatar_objs.append(oid)
+    if len(self.avatar_objs) != self.num_players:
+      raise ValueError('number of avatar objects != numPlayers')
+    self.world_sprite_map = sim.get('worldSpriteMap') or {}
+
+  # -------------------------------------------------------------------------
+  def _state_index(self, names: List[str], state: str) -> int:
+    if state not in names:
+      raise KeyError(f'state {state!r} not in {names}')
+    return names.index(state)
+
+  def _add_kind(self, cfg) -> int:
+    comps = cfg['components']
+    sm = _first(comps, 'StateManager')['kwargs']
+    names = [st['state'] for st in sm['stateConfigs']]
+    state0 = len(self.states)
+    for st in sm['stateConfigs']:
+      layer = self.layers.index(st['layer']) if isinstance(st.get('layer'), str) else -1
+      sprite = self.sprites.index(st['sprite']) if isinstance(st.get('sprite'), str) else -1
+      contact = 0 if isinstance(st.get('contact'), str) else -1
+      if isinstance(st.get('contact'), str) and st['contact'] != 'avatar':
+        raise NotImplementedError('only the "avatar" contact is supported')
+      mask = 0
+      for g in st.get('groups', []) or []:
+        mask |= 1 << self.groups.index(g)
+      self.states.append([layer, sprite, contact, mask])
+    comp0 = len(self.comps_i)
+    is_avatar = 0
+    for c in comps:
+      name = c['component']
+      kw = c.get('kwargs', {}) or {}
+      if name not in COMP:
+        raise NotImplementedError(
+            f'component {name!r} is not supported by the B200 engine')
+      ip = [0] * COMP_NI
+      dp = [0.0] * COMP_ND
+      si = lambda s: self._state_index(names, s)
+      hit_id = lambda h: [x[0] for x in self.hits].index(h)
+      if name == 'BeamBlocker':
+        ip[0] = hit_id(kw['beamType']) if kw['beamType'] in [h[0] for h in self.hits] else -1
+      elif name == 'Edible':
+        ip[0], ip[1] = si(kw['liveState']), si(kw['waitState'])
+        dp[0] = float(kw['rewardForEating'])
+      elif name == 'AppleGrow':
+        ip[0] = si('apple')
+        dp[0] = float(kw['maxAppleGrowthRate'])
+        dp[1] = float(kw['thresholdDepletion'])
+        dp[2] = float(kw['thresholdRestoration'])
+      elif name == 'DirtTracker':
+        ip[0] = si(kw.get('activeState', 'dirt'))
+        ip[1] = si(kw.get('inactiveState', 'dirtWait'))
+      elif name == 'DirtCleaning':
+        ip[0], ip[1], ip[2] = si('dirt'), si('dirtWait'), hit_id('cleanHit')
+      elif name == 'Avatar':
+        is_avatar = 1
+        idx0 = int(kw['index']) - 1
+        ip[0] = idx0
+        ip[1], ip[2] = si(kw['aliveState']), si(kw['waitState'])
+        ip[3] = self.groups.index(kw['spawnGroup'])
+        post = kw.get('postInitialSpawnGroup', '_DEFAULT')
+        ip[4] = -1 if post == '_DEFAULT' else self.groups.index(post)
+        view = kw['view']
+        ip[5:9] = [int(view['left']), int(view['right']), int(view['forward']),
+                   int(view['backward'])]
+        if view.get('centered', False):
+          raise NotImplementedError('centered views')
+        if self.view is None:
+          self.view = tuple(ip[5:9])
+        elif self.view != tuple(ip[5:9]):
+          raise NotImplementedError('per-avatar view sizes')
+        ip[9] = int(kw.get('skipWaitStateRewards', True))
+        ip[10] = int(kw.get('randomizeInitialOrientation', True))
+        dp[0] = float(kw.get('speed', 1.0))
+        if kw.get('useAbsoluteCoordinates', False):
+          raise NotImplementedError('useAbsoluteCoordinates')
+        if kw.get('additionalLiveStates'):
+          raise NotImplementedError('additionalLiveStates')
+        order = list(kw.get('actionOrder', ['move', 'turn']))
+        for a in order:
+          if a not in ACTION_FIELDS:
+            raise NotImplementedError(f'action {a!r}')
+        self.sprite_maps[idx0] = dict(kw.get('spriteMap', {}) or {})
+      elif name == 'Zapper':
+        ip[0], ip[1], ip[2] = int(kw['cooldownTime']), int(kw['beamLength']), int(kw['beamRadius'])
+        ip[3] = int(kw['framesTillRespawn'])
+        ip[4] = int(kw.get('removeHitPlayer', True))
+        ip[5] = hit_id('zapHit')
+        dp[0] = float(kw['penaltyForBeingZapped'])
+        dp[1] = float(kw['rewardForZapping'])
+      elif name == 'Cleaner':
+        ip[0], ip[1], ip[2] = int(kw['cooldownTime']), int(kw['beamLength']), int(kw['beamRadius'])
+        ip[3] = hit_id('cleanHit')
+      elif name == 'Taste':
+        ip[0] = _TASTE_ROLES[kw.get('role', 'free')]
+        dp[0] = float(kw.get('rewardAmount', 1))
+      elif name == 'DirtSpawner':
+        ip[0] = int(kw.get('delayStartOfDirtSpawning', 0))
+        dp[0] = float(kw['dirtSpawnProbability'])
+      elif name == 'StochasticIntervalEpisodeEnding':
+        ip[0] = int(kw['minimumFramesPerEpisode'])
+        ip[1] = int(kw['intervalLength'])
+        dp[0] = float(kw['probabilityTerminationPerInterval'])
+      elif name == 'Animation':
+        sts = list(kw['states'])
+        if len(sts) > 8:
+          raise NotImplementedError('Animation with > 8 states')
+        ip[0] = len(sts)
+        for i, s in enumerate(sts):
+          ip[1 + i] = si(s)
+        ip[9] = int(kw['gameFramesPerAnimationFrame'])
+        ip[10] = int(kw['loop'])
+        ip[11] = int(kw.get('randomStartFrame', False))
+      elif name == 'DensityRegrow':
+        ip[0] = si(kw['liveState'])
+        ip[3] = si(kw['waitState'])
+        radius = float(kw['radius'])
+        upper = int(np.floor(np.pi * radius**2 + 1)) + 1 if radius >= 0 else 0
+        ip[1] = si(kw['waitState'] + '_0')
+        ip[2] = upper
+        probs = [float(p) for p in kw['regrowthProbabilities']]
+        if len(probs) > COMP_ND - 1:
+          raise NotImplementedError('too many regrowthProbabilities')
+        ip[4] = len(probs)
+        ip[5] = int(kw.get('canRegrowIfOccupied', True))
+        dp[0] = radius
+        dp[1:1 + len(probs)] = probs
+      self.comps_i.append([COMP[name]] + ip)
+      self.comps_d.append(dp)
+    kid = len(self.kinds)
+    self.kinds.append([state0, len(names), comp0, len(comps), is_avatar, 0])
+    self.kind_names.append(cfg.get('name', ''))
+    self.state_names.append(names)
+    return kid
+
+  # -------------------------------------------------------------------------
+  def sprite_map_table(self) -> np.ndarray:
+    """[P+1, n_sprites]: viewer -> displayed sprite (row P = WORLD.RGB)."""
+    n = len(self.sprites.names)
+    table = np.tile(np.arange(n, dtype=np.int32), (self.num_players + 1, 1))
+    for idx0, mapping in self.sprite_maps.items():
+      for src, dst in mapping.items():
+        table[idx0, self.sprites.index(src)] = self.sprites.index(dst)
+    for src, dst in self.world_sprite_map.items():
+      table[self.num_players, self.sprites.index(src)] = self.sprites.index(dst)
+    return table
+
+  def init_grid(self) -> np.ndarray:
+    """uint16 [L, H*W]: sprites of all non-avatar objects in their initial state."""
+    L = len(self.layers)
+    grid = np.zeros((L, self.H * self.W), np.uint16)
+    occupied = np.zeros((L, self.H * self.W), bool)
+    for (kid, x, y, orient, st) in self.objects:
+      if self.kinds[kid][4]:
+        continue
+      layer, sprite, _, _ = self.states[self.kinds[kid][0] + st]
+      if layer < 0:
+        continue
+      cell = y * self.W + x
+      if occupied[layer, cell]:
+        raise ValueError(f'two pieces on layer {self.layers[layer]} at {x},{y}')
+      occupied[layer, cell] = True
+      if sprite >= 0:
+        grid[layer, cell] = 1 + sprite * 4 + orient
+    return grid
+
+
+# ---------------------------------------------------------------------------
+# Family tables for the CUDA engine
+# ---------------------------------------------------------------------------
+def _objects_with(model: WorldModel, comp: str):
+  out = []
+  for oid, (kid, x, y, orient, st) in enumerate(model.objects):
+    k = model.kinds[kid]
+    for ci in range(k[2], k[2] + k[3]):
+      if model.comps_i[ci][0] == COMP[comp]:
+        out.append((oid, ci))
+        break
+  return out
+
+
+def _avatar_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
+  """Tables shared by all families: avatars, spawn points, blockers."""
+  P = model.num_players
+  av = np.zeros((P, 8), np.int32)  # obj id, live sprite, layer, spawn group, post group
+  for oid in model.avatar_objs:
+    kid = model.objects[oid][0]
+    k = model.kinds[kid]
+    ci = [c for c in range(k[2], k[2] + k[3]) if model.comps_i[c][0] == COMP['Avatar']][0]
+    ip = model.comps_i[ci][1:]
+    idx0 = ip[0]
+    alive = model.states[k[0] + ip[1]]
+    av[idx0] = [oid, alive[1], alive[0], ip[3], ip[4], 0, 0, 0]
+  sections['av_table'] = av
+  # Spawn cells per group, in object (piece) order.
+  for gi, g in enumerate(model.groups):
+    cells = []
+    for (kid, x, y, orient, st) in model.objects:
+      state = model.states[model.kinds[kid][0] + st]
+      if state[3] & (1 << gi) and not model.kinds[kid][4]:
+        cells.append(y * model.W + x)
+    if g in ('spawnPoints', 'insideSpawnPoints'):
+      sections['spawn_cells_' + str(gi)] = np.array(cells, np.int32)
+  # Static beam blockers: bit h set if a BeamBlocker for hit h sits on the cell.
+  flags = np.zeros(model.H * model.W, np.uint8)
+  for oid, ci in _objects_with(model, 'BeamBlocker'):
+    kid, x, y, _, _ = model.objects[oid]
+    k = model.kinds[kid]
+    for c in range(k[2], k[2] + k[3]):
+      if model.comps_i[c][0] == COMP['BeamBlocker'] and model.comps_i[c][1] >= 0:
+        flags[y * model.W + x] |= 1 << model.comps_i[c][1]
+  sections['cell_flags'] = flags
+
+
+def _clean_up_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
+  """SoA tables for the clean_up step kernel."""
+  W = model.W
+  ip = np.zeros(48, np.int32)
+  dp = np.zeros(16, np.float64)
+  def entity(comp):
+    rows = []
+    for oid, ci in _objects_with(model, comp):
+      kid, x, y, orient, st = model.objects[oid]
+      rows.append((oid, y * W + x, st, kid, ci))
+    return rows
+  apples = entity('AppleGrow')
+  dirts = entity('DirtTracker')
+  waters = entity('Animation')
+  kid_a, ci_a = apples[0][3], apples[0][4]
+  for row in apples:
+    if row[3] != kid_a:
+      raise NotImplementedError('heterogeneous apple prefabs')
+  ka = model.kinds[kid_a]
+  apple_state = model.states[ka[0] + model.comps_i[ci_a][1]]
+  edible = [c for c in range(ka[2], ka[2] + ka[3]) if model.comps_i[c][0] == COMP['Edible']][0]
+  sections['cu_apple'] = np.array([[r[0], r[1], int(r[2] == model.comps_i[ci_a][1])] for r in apples], np.int32)
+  # Dirt: both prefabs share states; column 2 = initially dirty.
+  dirt_rows = []
+  dirt_layer = dirt_sprite = wait_layer = None
+  for r in dirts:
+    k = model.kinds[r[3]]
+    cip = model.comps_i[r[4]][1:]
+    active, inactive = cip[0], cip[1]
+    sa, sw = model.states[k[0] + active], model.states[k[0] + inactive]
+    if dirt_layer is None:
+      dirt_layer, dirt_sprite, wait_layer = sa[0], sa[1], sw[0]
+    elif (dirt_layer, dirt_sprite, wait_layer) != (sa[0], sa[1], sw[0]):
+      raise NotImplementedError('heterogeneous dirt prefabs')
+    dirt_rows.append([r[0], r[1], int(r[2] == active)])
+  sections['cu_dirt'] = np.array(dirt_rows, np.int32)
+  kw_ = model.kinds[waters[0][3]]
+  anim = model.comps_i[waters[0][4]][1:]
+  n_anim = anim[0]
+  water_sprites = [model.states[kw_[0] + anim[1 + i]][1] for i in range(n_anim)]
+  water_layer = model.states[kw_[0] + anim[1]][0]
+  sections['cu_water'] = np.array([[r[0], r[1]] for r in waters], np.int32)
+  sections['cu_water_sprites'] = np.array(water_sprites, np.int32)
+  # Avatar components (identical kwargs across avatars are required).
+  def avatar_comp(comp):
+    rows = []
+    for oid in model.avatar_objs:
+      k = model.kinds[model.objects[oid][0]]
+      ci = [c for c in range(k[2], k[2] + k[3]) if model.comps_i[c][0] == COMP[comp]][0]
+      rows.append((model.comps_i[ci][1:], model.comps_d[ci]))
+    for r in rows[1:]:
+      if comp != 'Avatar' and r != rows[0]:
+        raise NotImplementedError(f'per-avatar {comp} parameters')
+    return rows[0]
+  zi, zd = avatar_comp('Zapper')
+  ci_, _ = avatar_comp('Cleaner')
+  ti, td = avatar_comp('Taste')
+  scene_k = model.kinds[model.objects[0][0]]
+  def scene_comp(comp):
+    for c in range(scene_k[2], scene_k[2] + scene_k[3]):
+      if model.comps_i[c][0] == COMP[comp]:
+        return model.comps_i[c][1:], model.comps_d[c]
+    raise KeyError(comp)
+  si_, sd_ = scene_comp('DirtSpawner')
+  ei_, ed_ = scene_comp('StochasticIntervalEpisodeEnding')
+  hits = {h[0]: (model.layers.index(h[1]), model.sprites.index(h[2])) for h in model.hits}
+  ip[0:8] = [len(apples), len(dirts), len(waters), apple_state[0], apple_state[1],
+             dirt_layer, dirt_sprite, wait_layer]
+  ip[8:12] = [water_layer, n_anim, anim[9], anim[11]]
+  ip[12:18] = [zi[0], zi[1], zi[2], zi[3], zi[4], 0]          # zapper
+  ip[18:21] = [ci_[0], ci_[1], ci_[2]]                       # cleaner
+  ip[21:25] = [hits['zapHit'][0], hits['zapHit'][1], hits['cleanHit'][0], hits['cleanHit'][1]]
+  ip[25] = si_[0]
+  ip[26:28] = [ei_[0], ei_[1]]
+  ip[28] = ti[0]
+  ip[29] = 0  # scene object id
+  ag = model.comps_d[ci_a]
+  dp[0:3] = ag[0:3]
+  dp[3] = model.comps_d[edible][0]
+  dp[4], dp[5] = zd[0], zd[1]
+  dp[6] = sd_[0]
+  dp[7] = ed_[0]
+  dp[8] = td[0]
+  sections['cu_ip'] = ip
+  sections['cu_dp'] = dp
+
+
+# ---------------------------------------------------------------------------
+# Entry points
+# ---------------------------------------------------------------------------
+def compile_settings(settings: Mapping[str, Any],
+                     config: Optional[Any] = None) -> bytes:
+  """lab2d settings (+ optional substrate config for API metadata) -> blob."""
+  model = WorldModel(settings)
+  P = model.num_players
+  meta = np.zeros(META_COUNT, np.int32)
+  atlas = model.sprites.atlas()
+  action_set = [dict(a) for a in _plain(config.action_set)] if config is not None else []
+  fields = sorted({ACTION_FIELDS[k] for a in action_set for k in a}) or [0, 1]
+  n_fields = max(fields) + 1
+  action_table = np.zeros((max(len(action_set), 1), 4), np.int32)
+  for i, a in enumerate(action_set):
+    for k, v in a.items():
+      action_table[i, ACTION_FIELDS[k]] = int(v)
+  indiv = list(config.individual_observation_names) if config is not None else ['RGB']
+  globs = list(config.global_observation_names) if config is not None else ['WORLD.RGB']
+  scalar_obs = []
+  for name in indiv:
+    if name == 'RGB':
+      continue
+    if name not in SCALAR_OBS:
+      raise NotImplementedError(f'observation {name!r}')
+    scalar_obs.append(SCALAR_OBS[name])
+  for name in globs:
+    if name != 'WORLD.RGB':
+      raise NotImplementedError(f'global observation {name!r}')
+  vals = dict(FAMILY=FAMILY[model.family], W=model.W, H=model.H,
+              L=len(model.layers), P=P, SPRITE_SIZE=model.sprite_size,
+              TOPOLOGY=model.topology, MAX_FRAMES=model.max_frames,
+              N_OBJECTS=len(model.objects), N_KINDS=len(model.kinds),
+              N_STATES=len(model.states), N_COMPS=len(model.comps_i),
+              N_SPRITES=len(model.sprites.names), N_HITS=len(model.hits),
+              N_GROUPS=len(model.groups), VIEW_LEFT=model.view[0],
+              VIEW_RIGHT=model.view[1], VIEW_FORWARD=model.view[2],
+              VIEW_BACKWARD=model.view[3], N_ACTIONS=len(action_set),
+              N_ACTION_FIELDS=n_fields,
+              OOB_SPRITE=model.sprites.index('OutOfBounds'),
+              OOV_SPRITE=model.sprites.index('OutOfView'),
+              N_SCALAR_OBS=len(scalar_obs))
+  for k, v in vals.items():
+    meta[META[k]] = v
+  opaque = (atlas[..., 3] == 255).all(axis=(1, 2, 3)).astype(np.uint8)
+  sections: Dict[str, Any] = {
+      'meta': meta,
+      'atlas': atlas.reshape(len(model.sprites.names), 4, -1),
+      'sprite_opaque': opaque,
+      'states': np.array(model.states, np.int32),
+      'kinds': np.array(model.kinds, np.int32),
+      'comps': np.array(model.comps_i, np.int32),
+      'comps_f': np.array(model.comps_d, np.float64),
+      'objects': np.array(model.objects, np.int32),
+      'hits': np.array([[model.layers.index(h[1]), model.sprites.index(h[2])]
+                        for h in model.hits], np.int32).reshape(-1, 2),
+      'action_table': action_table,
+      'sprite_map': model.sprite_map_table(),
+      'scalar_obs': np.array(scalar_obs, np.int32),
+      'init_grid': model.init_grid(),
+  }
+  _avatar_tables(model, sections)
+  if model.family == 'clean_up':
+    _clean_up_tables(model, sections)
+  info = dict(
+      level=model.level, family=model.family, layers=model.layers,
+      sprites=model.sprites.names, groups=model.groups,
+      hits=[h[0] for h in model.hits], kinds=model.kind_names,
+      kind_states=model.state_names, num_players=P,
+      individual_observation_names=indiv, global_observation_names=globs,
+      action_set=action_set,
+      world_rgb_shape=[model.H * model.sprite_size, model.W * model.sprite_size, 3],
+      rgb_shape=[(model.view[2] + model.view[3] + 1) * model.sprite_size,
+                 (model.view[0] + model.view[1] + 1) * model.sprite_size, 3],
+      valid_roles=sorted(config.valid_roles) if config is not None else [],
+      default_player_roles=list(config.default_player_roles) if config is not None else [],
+  )
+  sections['info_json'] = json.dumps(info)
+  return blob_lib.pack(sections)
+
+
+def compile_substrate(name: str, roles: Optional[Sequence[str]] = None,
+                      root: Optional[str] = None) -> bytes:
+  """Compiles a named reference substrate (needs a reference checkout)."""
+  config = load_reference_config(name, root)
+  roles = tuple(roles) if roles is not None else tuple(config.default_player_roles)
+  settings = config.lab2d_settings_builder(roles=roles, config=config)
+  return compile_settings(settings, config)

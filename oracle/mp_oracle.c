@@ -1,0 +1,819 @@
+/* mp_oracle.c -- CPU restatement of the Melting Pot hot path (TEST INFRASTRUCTURE ONLY).
+ *
+ * PARITY UNPINNED: the arithmetic of this path lives in the third-party engine
+ * dmlab2d==1.0.0 (/root/reference/requirements.txt:339), which is neither vendored nor
+ * installable here, and the reference's tests hold no golden pixels / reward traces / RNG
+ * known-answers for it. This file restates
+ *   (1) the Melting Pot Lua scheduling + components, citing file:line for every function, and
+ *   (2) the engine rules they rely on, as the named policies of DESIGN.md "Engine policy ledger"
+ *       (SURVEY.md Appendix A), each implemented in exactly one function below.
+ * What IS pinned: Philox4x32-10 known answers (Random123), and the behaviours the reference's
+ * Lua tests state (game_object_test.lua:252-411) -- see tests/test_oracle_semantics.py.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library.
+ * The product (meltingpot_b200/csrc) shares no code with it except include/mpb_format.h
+ * (the blob layout).
+ *
+ * Structure mirrors the reference: an engine core (pieces on a layered grid, a deferred action
+ * queue, contact/hit/state callbacks -- docs/advanced.md:7-56) and components dispatched by type.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/mpb_format.h"
+
+#define OR_MAX_PLAYERS 16
+#define OR_MAX_LAYERS 16
+#define OR_MAX_ROUNDS 128 /* policy A.4: grid:update flushCount */
+
+/* ------------------------------------------------------------------------------------------
+ * RNG: Philox4x32-10 (Salmon et al., SC'11), counter-based so that the CUDA engine can draw
+ * the same numbers in any schedule. Policy A.16: the reference's mt19937_64 stream is out of
+ * reach; every draw is addressed by (seed, episode, frame, stream, index).
+ * ---------------------------------------------------------------------------------------- */
+enum { RS_SCENE = 0, RS_AVATAR = 1, RS_OBJECT = 2, RS_AVATAR_RESET = 3, RS_OBJECT_RESET = 4 };
+enum { SCENE_DRAW_DIRT = 0, SCENE_DRAW_EPISODE_END = 1 };
+
+static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_10(ctr, key, out); }
+
+static inline double u01(uint32_t a, uint32_t b) { /* 53-bit uniform in [0,1) */
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+static inline uint32_t pick(uint32_t w, uint32_t n) { return (uint32_t)(((uint64_t)w * n) >> 32); }
+
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { int layer, sprite, contact; uint32_t groups; } StateDef;
+typedef struct { int type; int ip[MPB_COMP_NI]; double dp[MPB_COMP_ND]; } CompDef;
+typedef struct { int state0, n_states, comp0, n_comps, is_avatar; } KindDef;
+
+typedef struct {
+  int kind, state, x, y, orient;
+  int layer;       /* current layer, -1 = off grid (policy A.1) */
+  int state_frame; /* grid frame at which the current state was entered */
+  int prev_state;
+  /* component variables */
+  int act[4];
+  double reward;
+  int movement_allowed, freeze, removal;              /* Avatar */
+  int spawn_group;
+  int zap_cool;                                      /* Zapper */
+  int clean_cool, player_cleaned;                    /* Cleaner */
+  int player_ate;                                    /* Taste */
+  int num_others_cleaned, num_others_ate;            /* AllNonselfCumulants */
+} Obj;
+
+enum { ACT_SET_STATE, ACT_TURN, ACT_MOVE_REL, ACT_TELEPORT_GROUP, ACT_BEAM };
+typedef struct { int type, obj, a, b, c; } Action;
+
+enum { EV_ZAP = 1, EV_EDIBLE_CONSUMED = 2, EV_PLAYER_CLEANED = 3 };
+typedef struct { int type, a, b; } Event;
+
+enum { /* updater function ids */
+  UF_AVATAR_MOVE, UF_ZAP, UF_RESPAWN, UF_CLEAN, UF_CLEANER_RESET, UF_TASTE_RESET, UF_NONSELF_GET,
+  UF_NONSELF_RESET, UF_GLOBAL_RESET, UF_EPISODE_END, UF_ANIMATION
+};
+typedef struct { int priority, comp_type, fn, seq; } Updater;
+
+typedef struct OrEnv {
+  /* static tables */
+  int W, H, L, P, S, topology, max_frames, n_obj, n_kinds, n_sprites, n_hits, n_groups;
+  int view_l, view_r, view_f, view_b, n_actions, oob_sprite, oov_sprite, n_scalar;
+  StateDef* states; KindDef* kinds; CompDef* comps; int* objdef; int* hits; int* action_table;
+  int* sprite_map; int* scalar_obs; uint8_t* atlas; uint8_t* sprite_opaque;
+  int avatar_obj[OR_MAX_PLAYERS];
+  Updater* updaters; int n_updaters;
+  /* dynamic */
+  uint32_t key[2];
+  int episode, frame, step, cont, done, step_type;
+  Obj* obj;
+  int* grid;   /* [L][cells] obj id + 1 */
+  uint16_t* beam; /* [L][cells] temporary hit sprites (MPB_CELL) */
+  Action* q; int qn, qcap; Action* qnext; int qnn, qncap;
+  Event* ev; int evn, evcap;
+  int order[OR_MAX_PLAYERS]; /* avatar processing order this frame */
+  /* scene component variables */
+  int dirt_count, clean_count, spawner_t, ending_t;
+  int cleaned_flag[OR_MAX_PLAYERS], ate_flag[OR_MAX_PLAYERS];
+} OrEnv;
+
+static const int DX[4] = {0, 1, 0, -1}, DY[4] = {-1, 0, 1, 0}; /* N E S W (component_library.lua:38-43) */
+
+static void rng(const OrEnv* e, int stream, int index, uint32_t out[4]) {
+  uint32_t ctr[4] = {(uint32_t)e->frame, (uint32_t)e->episode, (uint32_t)index, (uint32_t)stream};
+  philox4x32_10(ctr, e->key, out);
+}
+
+static inline const KindDef* kind_of(const OrEnv* e, const Obj* o) { return &e->kinds[o->kind]; }
+static inline const StateDef* state_def(const OrEnv* e, const Obj* o, int s) { return &e->states[kind_of(e, o)->state0 + s]; }
+static const CompDef* find_comp(const OrEnv* e, const Obj* o, int type) {
+  const KindDef* k = kind_of(e, o);
+  for (int i = 0; i < k->n_comps; ++i) if (e->comps[k->comp0 + i].type == type) return &e->comps[k->comp0 + i];
+  return 0;
+}
+static inline int cell_of(const OrEnv* e, int x, int y) { return y * e->W + x; }
+
+static void enqueue(OrEnv* e, int type, int obj, int a, int b, int c) {
+  if (e->qnn == e->qncap) { e->qncap = e->qncap ? e->qncap * 2 : 256; e->qnext = (Action*)realloc(e->qnext, sizeof(Action) * e->qncap); }
+  Action act = {type, obj, a, b, c};
+  e->qnext[e->qnn++] = act;
+}
+static void add_event(OrEnv* e, int type, int a, int b) {
+  if (e->evn == e->evcap) { e->evcap = e->evcap ? e->evcap * 2 : 64; e->ev = (Event*)realloc(e->ev, sizeof(Event) * e->evcap); }
+  Event ev = {type, a, b};
+  e->ev[e->evn++] = ev;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Components: callbacks. Each cites the Lua it restates.
+ * ---------------------------------------------------------------------------------------- */
+/* Avatar:addReward -- avatar_library.lua:364-378 */
+static void avatar_add_reward(OrEnv* e, Obj* av, double amount) {
+  const CompDef* c = find_comp(e, av, MPB_C_AVATAR);
+  if (c->ip[9] /* skipWaitStateRewards */ && av->state == c->ip[2]) return;
+  av->reward += amount;
+}
+static int avatar_is_alive(const OrEnv* e, const Obj* av) { /* avatar_library.lua:493-495 */
+  return av->state == find_comp(e, av, MPB_C_AVATAR)->ip[1];
+}
+
+/* GameObject:_onEnter -> component onEnter (game_object.lua:316-318). */
+static void on_enter(OrEnv* e, int target, int initiator) {
+  Obj* t = &e->obj[target]; Obj* ini = &e->obj[initiator];
+  const CompDef* ed = find_comp(e, t, MPB_C_EDIBLE);
+  if (ed) { /* Edible:onEnter -- clean_up/components.lua:390-408 ; component_library.lua:990-1002 */
+    if (t->state == ed->ip[0]) {
+      const CompDef* taste = find_comp(e, ini, MPB_C_TASTE);
+      const CompDef* avc = find_comp(e, ini, MPB_C_AVATAR);
+      if (taste) { /* Taste:consumed -- clean_up/components.lua:446-455 */
+        if (taste->ip[0] == 1) avatar_add_reward(e, ini, 0.0);
+        else if (taste->ip[0] == 2) avatar_add_reward(e, ini, taste->dp[0]);
+        else avatar_add_reward(e, ini, ed->dp[0]);
+        ini->player_ate += 1;                 /* Taste:setCumulant :457-464 */
+        e->ate_flag[avc->ip[0]] = 1;          /* GlobalData:setAteThisStep :498-500 */
+      } else {
+        avatar_add_reward(e, ini, ed->dp[0]);
+      }
+      add_event(e, EV_EDIBLE_CONSUMED, avc->ip[0] + 1, 0);
+      enqueue(e, ACT_SET_STATE, target, ed->ip[1], 0, 0);
+    }
+  }
+}
+
+/* GameObject:_onHit: any component returning true blocks the beam (game_object.lua:305-314). */
+static int on_hit(OrEnv* e, int target, int shooter, int hit) {
+  Obj* t = &e->obj[target]; Obj* sh = &e->obj[shooter];
+  const KindDef* k = kind_of(e, t);
+  int blocked = 0;
+  for (int i = 0; i < k->n_comps; ++i) {
+    const CompDef* c = &e->comps[k->comp0 + i];
+    switch (c->type) {
+      case MPB_C_BEAM_BLOCKER: /* component_library.lua:678-685 */
+        if (c->ip[0] == hit) blocked = 1;
+        break;
+      case MPB_C_ZAPPER: /* Zapper:onHit -- avatar_library.lua:652-681 */
+        if (hit == c->ip[5]) {
+          const CompDef* tav = find_comp(e, t, MPB_C_AVATAR);
+          const CompDef* sav = find_comp(e, sh, MPB_C_AVATAR);
+          add_event(e, EV_ZAP, sav->ip[0] + 1, tav->ip[0] + 1);
+          avatar_add_reward(e, t, c->dp[0]);
+          avatar_add_reward(e, sh, c->dp[1]);
+          if (c->ip[4]) enqueue(e, ACT_SET_STATE, target, tav->ip[2], 0, 0);
+          blocked = 1;
+        }
+        break;
+      case MPB_C_DIRT_CLEANING: /* DirtCleaning:onHit -- clean_up/components.lua:141-157 */
+        if (t->state == c->ip[0] && hit == c->ip[2]) {
+          enqueue(e, ACT_SET_STATE, target, c->ip[1], 0, 0);
+          const CompDef* taste = find_comp(e, sh, MPB_C_TASTE);
+          if (taste) { /* Taste:cleaned :437-444 */
+            if (taste->ip[0] == 1) avatar_add_reward(e, sh, taste->dp[0]);
+            if (taste->ip[0] == 2) avatar_add_reward(e, sh, 0.0);
+          }
+          const CompDef* sav = find_comp(e, sh, MPB_C_AVATAR);
+          if (find_comp(e, sh, MPB_C_CLEANER)) { /* Cleaner:setCumulant :248-255 */
+            sh->player_cleaned += 1;
+            e->cleaned_flag[sav->ip[0]] = 1;
+          }
+          add_event(e, EV_PLAYER_CLEANED, sav->ip[0] + 1, 0);
+          blocked = 1;
+        }
+        break;
+      default: break;
+    }
+  }
+  return blocked;
+}
+
+/* GameObject:_onAdd -> component onStateChange(previousState) (game_object.lua:273-285). */
+static void on_state_change(OrEnv* e, int oi, int old_state) {
+  Obj* o = &e->obj[oi];
+  const KindDef* k = kind_of(e, o);
+  for (int i = 0; i < k->n_comps; ++i) {
+    const CompDef* c = &e->comps[k->comp0 + i];
+    switch (c->type) {
+      case MPB_C_DIRT_TRACKER: /* clean_up/components.lua:118-129 */
+        if (old_state == c->ip[1] && o->state == c->ip[0]) { e->dirt_count++; e->clean_count--; }
+        else if (old_state == c->ip[0] && o->state == c->ip[1]) { e->dirt_count--; e->clean_count++; }
+        break;
+      case MPB_C_AVATAR: /* avatar_library.lua:430-453 */
+        if (old_state == c->ip[2] && o->state == c->ip[1]) { o->freeze = 0; o->removal = 0; }
+        break;
+      default: break;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Engine core (policies A.1-A.9 of the ledger).
+ * ---------------------------------------------------------------------------------------- */
+static void lift(OrEnv* e, int oi) {
+  Obj* o = &e->obj[oi];
+  if (o->layer >= 0) { e->grid[o->layer * e->W * e->H + cell_of(e, o->x, o->y)] = 0; }
+}
+static void place(OrEnv* e, int oi) {
+  Obj* o = &e->obj[oi];
+  if (o->layer >= 0) e->grid[o->layer * e->W * e->H + cell_of(e, o->x, o->y)] = oi + 1;
+}
+/* Policy A.5: placing a piece fires contact `enter` both ways with every other piece on the cell. */
+static void trigger_enter(OrEnv* e, int oi) {
+  Obj* o = &e->obj[oi];
+  if (o->layer < 0) return;
+  int cell = cell_of(e, o->x, o->y), cells = e->W * e->H;
+  int my_contact = state_def(e, o, o->state)->contact;
+  for (int l = 0; l < e->L; ++l) {
+    int q = e->grid[l * cells + cell] - 1;
+    if (q < 0 || q == oi) continue;
+    if (my_contact >= 0) on_enter(e, q, oi);
+    if (state_def(e, &e->obj[q], e->obj[q].state)->contact >= 0) on_enter(e, oi, q);
+  }
+}
+/* grid:setState (component_library.lua:194-198). Policy A.18: same-state is a no-op; policy A.2. */
+static void do_set_state(OrEnv* e, int oi, int ns) {
+  Obj* o = &e->obj[oi];
+  if (ns == o->state) return;
+  int nl = state_def(e, o, ns)->layer;
+  if (nl >= 0) {
+    int occ = e->grid[nl * e->W * e->H + cell_of(e, o->x, o->y)] - 1;
+    if (occ >= 0 && occ != oi) return; /* blocked: stays as it was (onBlocked has no listeners) */
+  }
+  int old = o->state;
+  lift(e, oi);
+  o->prev_state = old; o->state = ns; o->layer = nl; o->state_frame = e->frame;
+  place(e, oi);
+  on_state_change(e, oi, old);
+  trigger_enter(e, oi);
+}
+static void do_turn(OrEnv* e, int oi, int k) { /* policy A.6 */
+  Obj* o = &e->obj[oi];
+  if (o->layer < 0) return;
+  o->orient = (o->orient + k) & 3;
+}
+static int wrap_or_reject(const OrEnv* e, int* x, int* y) {
+  if (e->topology == 1) { *x = ((*x % e->W) + e->W) % e->W; *y = ((*y % e->H) + e->H) % e->H; return 1; }
+  return *x >= 0 && *x < e->W && *y >= 0 && *y < e->H;
+}
+/* grid:moveRel (component_library.lua:320-322): lift, attempt, place (docs/advanced.md:45-52). */
+static void do_move_rel(OrEnv* e, int oi, int rel) {
+  Obj* o = &e->obj[oi];
+  if (o->layer < 0) return;
+  int d = (o->orient + rel) & 3;
+  int nx = o->x + DX[d], ny = o->y + DY[d];
+  lift(e, oi);
+  if (wrap_or_reject(e, &nx, &ny) && e->grid[o->layer * e->W * e->H + cell_of(e, nx, ny)] == 0) { o->x = nx; o->y = ny; }
+  place(e, oi);
+  trigger_enter(e, oi); /* fires even when the move was blocked */
+}
+/* grid:teleportToGroup (component_library.lua:351-354). Policy A.9. */
+static void do_teleport_group(OrEnv* e, int oi, int group, int ns) {
+  Obj* o = &e->obj[oi];
+  const CompDef* av = find_comp(e, o, MPB_C_AVATAR);
+  uint32_t w[4];
+  rng(e, RS_AVATAR, av ? av->ip[0] : oi, w);
+  int n = 0;
+  for (int i = 0; i < e->n_obj; ++i) {
+    const Obj* c = &e->obj[i];
+    if (c->layer >= 0 && (state_def(e, c, c->state)->groups & (1u << group))) ++n;
+  }
+  if (n == 0) return;
+  int k = (int)pick(w[1], (uint32_t)n), target = -1;
+  for (int i = 0; i < e->n_obj; ++i) {
+    const Obj* c = &e->obj[i];
+    if (c->layer >= 0 && (state_def(e, c, c->state)->groups & (1u << group))) { if (k-- == 0) { target = i; break; } }
+  }
+  int tx = e->obj[target].x, ty = e->obj[target].y;
+  int nl = state_def(e, o, ns)->layer;
+  if (nl >= 0) {
+    int occ = e->grid[nl * e->W * e->H + cell_of(e, tx, ty)] - 1;
+    if (occ >= 0 && occ != oi) return; /* blocked; the respawn updater fires again next frame */
+  }
+  int old = o->state;
+  lift(e, oi);
+  o->x = tx; o->y = ty; o->orient = (int)(w[2] & 3u); /* TELEPORT_ORIENTATION.PICK_RANDOM */
+  o->prev_state = old; o->state = ns; o->layer = nl; o->state_frame = e->frame;
+  place(e, oi);
+  if (old != ns) on_state_change(e, oi, old);
+  trigger_enter(e, oi);
+}
+/* One beam cell: onHit on every piece of the cell, then the hit sprite if not blocked.
+ * Returns 1 if the ray stops here. Policy A.8. */
+static int beam_cell(OrEnv* e, int shooter, int hit, int x, int y) {
+  if (!wrap_or_reject(e, &x, &y)) return 1;
+  int cells = e->W * e->H, cell = cell_of(e, x, y), blocked = 0;
+  for (int l = 0; l < e->L; ++l) {
+    int q = e->grid[l * cells + cell] - 1;
+    if (q < 0 || q == shooter) continue;
+    if (on_hit(e, q, shooter, hit)) blocked = 1;
+  }
+  if (blocked) return 1;
+  int hl = e->hits[hit * 2 + MPB_HIT_LAYER], hs = e->hits[hit * 2 + MPB_HIT_SPRITE];
+  if (e->beam[hl * cells + cell] == 0) e->beam[hl * cells + cell] = MPB_CELL(hs, e->obj[shooter].orient);
+  return 0;
+}
+/* grid:hitBeam(piece, hit, length, radius) (game_object.lua:253-258); geometry mirrors
+ * Zapper:getWhoZappable (avatar_library.lua:785-821). Policy A.8. */
+static void do_beam(OrEnv* e, int oi, int hit, int length, int radius) {
+  Obj* o = &e->obj[oi];
+  if (o->layer < 0) return;
+  int f = o->orient, fx = DX[f], fy = DY[f];
+  for (int i = 1; i <= length; ++i) if (beam_cell(e, oi, hit, o->x + fx * i, o->y + fy * i)) break;
+  for (int side = 0; side < 2; ++side) {
+    int s = side == 0 ? (f + 3) & 3 : (f + 1) & 3; /* left, then right */
+    for (int k = 1; k <= radius; ++k) {
+      int bx = o->x + DX[s] * k, by = o->y + DY[s] * k;
+      if (beam_cell(e, oi, hit, bx, by)) break;
+      for (int i = 1; i <= length - k; ++i) if (beam_cell(e, oi, hit, bx + fx * i, by + fy * i)) break;
+    }
+  }
+}
+
+static void process_queue(OrEnv* e) { /* policy A.4: rounds until empty, at most flushCount */
+  for (int round = 0; round < OR_MAX_ROUNDS && e->qnn > 0; ++round) {
+    Action* tmp = e->q; e->q = e->qnext; e->qnext = tmp;
+    int tcap = e->qcap; e->qcap = e->qncap; e->qncap = tcap;
+    e->qn = e->qnn; e->qnn = 0;
+    for (int i = 0; i < e->qn; ++i) {
+      Action a = e->q[i];
+      switch (a.type) {
+        case ACT_SET_STATE: do_set_state(e, a.obj, a.a); break;
+        case ACT_TURN: do_turn(e, a.obj, a.a); break;
+        case ACT_MOVE_REL: do_move_rel(e, a.obj, a.a); break;
+        case ACT_TELEPORT_GROUP: do_teleport_group(e, a.obj, a.a, a.b); break;
+        case ACT_BEAM: do_beam(e, a.obj, a.a, a.b, a.c); break;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Updaters (updater_registry.lua:114-159; priorities in SURVEY.md section 3.3).
+ * ---------------------------------------------------------------------------------------- */
+static void run_updater(OrEnv* e, const Updater* u, int oi) {
+  Obj* o = &e->obj[oi];
+  const CompDef* c = find_comp(e, o, u->comp_type);
+  int age = e->frame - o->state_frame;
+  switch (u->fn) {
+    case UF_AVATAR_MOVE: { /* avatar_library.lua:156-171 */
+      if (!o->movement_allowed) break;
+      if (o->act[MPB_ACT_TURN] != 0) enqueue(e, ACT_TURN, oi, o->act[MPB_ACT_TURN], 0, 0);
+      if (o->act[MPB_ACT_MOVE] != 0) enqueue(e, ACT_MOVE_REL, oi, o->act[MPB_ACT_MOVE] - 1, 0, 0);
+    } break;
+    case UF_ZAP: { /* avatar_library.lua:613-631 */
+      if (!avatar_is_alive(e, o) || c->ip[0] < 0) break;
+      if (o->zap_cool > 0) o->zap_cool--;
+      else if (o->act[MPB_ACT_FIRE_ZAP] == 1) { o->zap_cool = c->ip[0]; enqueue(e, ACT_BEAM, oi, c->ip[5], c->ip[1], c->ip[2]); }
+    } break;
+    case UF_RESPAWN: { /* avatar_library.lua:638-649: state = waitState, startFrame = framesTillRespawn */
+      const CompDef* av = find_comp(e, o, MPB_C_AVATAR);
+      if (o->state != av->ip[2] || age < c->ip[3]) break;
+      enqueue(e, ACT_TELEPORT_GROUP, oi, o->spawn_group, av->ip[1], 0);
+    } break;
+    case UF_CLEAN: { /* clean_up/components.lua:201-219 */
+      if (!avatar_is_alive(e, o) || c->ip[0] < 0) break;
+      if (o->clean_cool > 0) o->clean_cool--;
+      else if (o->act[MPB_ACT_FIRE_2] == 1) { o->clean_cool = c->ip[0]; enqueue(e, ACT_BEAM, oi, c->ip[3], c->ip[1], c->ip[2]); }
+    } break;
+    case UF_CLEANER_RESET: o->player_cleaned = 0; break;   /* clean_up/components.lua:226-232 */
+    case UF_TASTE_RESET: o->player_ate = 0; break;          /* :428-434 */
+    case UF_NONSELF_GET: { /* :535-545, sumNonself :524-531 */
+      int me = find_comp(e, o, MPB_C_AVATAR)->ip[0], sc = 0, sa = 0;
+      for (int p = 0; p < e->P; ++p) if (p != me) { sc += e->cleaned_flag[p]; sa += e->ate_flag[p]; }
+      o->num_others_cleaned = sc; o->num_others_ate = sa;
+    } break;
+    case UF_NONSELF_RESET: o->num_others_cleaned = 0; o->num_others_ate = 0; break; /* :547-556 */
+    case UF_GLOBAL_RESET: /* :484-491 */
+      for (int p = 0; p < e->P; ++p) { e->cleaned_flag[p] = 0; e->ate_flag[p] = 0; }
+      break;
+    case UF_EPISODE_END: { /* component_library.lua:927-940 */
+      if (age < c->ip[0]) break;
+      if (e->ending_t % c->ip[1] == 0) {
+        uint32_t w[4]; rng(e, RS_SCENE, SCENE_DRAW_EPISODE_END, w);
+        if (u01(w[0], w[1]) < c->dp[0]) e->cont = 0; /* simulation:endEpisode() */
+      }
+    } break;
+    case UF_ANIMATION: { /* component_library.lua:1070-1094: one updater per state, startFrame */
+      if (age < c->ip[9]) break;
+      int n = c->ip[0];
+      for (int i = 0; i < n; ++i) if (c->ip[1 + i] == o->state) {
+        if (i + 1 < n) enqueue(e, ACT_SET_STATE, oi, c->ip[2 + i], 0, 0);
+        else if (c->ip[10]) enqueue(e, ACT_SET_STATE, oi, c->ip[1], 0, 0);
+        break;
+      }
+    } break;
+  }
+}
+
+static void add_updater(OrEnv* e, int priority, int comp_type, int fn) {
+  for (int i = 0; i < e->n_updaters; ++i) if (e->updaters[i].comp_type == comp_type && e->updaters[i].fn == fn) return;
+  e->updaters = (Updater*)realloc(e->updaters, sizeof(Updater) * (e->n_updaters + 1));
+  Updater u = {priority, comp_type, fn, e->n_updaters};
+  e->updaters[e->n_updaters++] = u;
+}
+static int cmp_updater(const void* a, const void* b) {
+  const Updater* x = (const Updater*)a; const Updater* y = (const Updater*)b;
+  if (x->priority != y->priority) return y->priority - x->priority; /* descending (updater_registry.lua:163-170) */
+  return x->seq - y->seq; /* policy A.7: ties in first-registration order */
+}
+static void build_updaters(OrEnv* e) {
+  for (int oi = 0; oi < e->n_obj; ++oi) {
+    const KindDef* k = &e->kinds[e->objdef[oi * MPB_OBJ_COLS + MPB_OBJ_KIND]];
+    for (int i = 0; i < k->n_comps; ++i) {
+      switch (e->comps[k->comp0 + i].type) {
+        case MPB_C_AVATAR: add_updater(e, 150, MPB_C_AVATAR, UF_AVATAR_MOVE); break;
+        case MPB_C_ZAPPER: add_updater(e, 140, MPB_C_ZAPPER, UF_ZAP); add_updater(e, 135, MPB_C_ZAPPER, UF_RESPAWN); break;
+        case MPB_C_CLEANER: add_updater(e, 140, MPB_C_CLEANER, UF_CLEAN); add_updater(e, 400, MPB_C_CLEANER, UF_CLEANER_RESET); break;
+        case MPB_C_TASTE: add_updater(e, 400, MPB_C_TASTE, UF_TASTE_RESET); break;
+        case MPB_C_ALL_NONSELF_CUMULANTS: add_updater(e, 4, MPB_C_ALL_NONSELF_CUMULANTS, UF_NONSELF_GET); add_updater(e, 400, MPB_C_ALL_NONSELF_CUMULANTS, UF_NONSELF_RESET); break;
+        case MPB_C_GLOBAL_DATA: add_updater(e, 2, MPB_C_GLOBAL_DATA, UF_GLOBAL_RESET); break;
+        case MPB_C_STOCHASTIC_INTERVAL_EPISODE_ENDING: add_updater(e, 100, MPB_C_STOCHASTIC_INTERVAL_EPISODE_ENDING, UF_EPISODE_END); break;
+        case MPB_C_ANIMATION: add_updater(e, 100, MPB_C_ANIMATION, UF_ANIMATION); break;
+        default: break;
+      }
+    }
+  }
+  qsort(e->updaters, e->n_updaters, sizeof(Updater), cmp_updater);
+}
+
+/* Policy A.7: avatars are visited in a fresh random order every frame (the engine shuffles group
+ * members); all other objects in creation order. Order = ascending (philox word 0, index). */
+static void draw_avatar_order(OrEnv* e) {
+  uint32_t keyv[OR_MAX_PLAYERS];
+  for (int p = 0; p < e->P; ++p) { uint32_t w[4]; rng(e, RS_AVATAR, p, w); keyv[p] = w[0]; e->order[p] = p; }
+  for (int i = 1; i < e->P; ++i) { /* insertion sort by (key, index) */
+    int v = e->order[i], j = i - 1;
+    while (j >= 0 && (keyv[e->order[j]] > keyv[v] || (keyv[e->order[j]] == keyv[v] && e->order[j] > v))) { e->order[j + 1] = e->order[j]; --j; }
+    e->order[j + 1] = v;
+  }
+}
+
+/* grid:update(random) -- api_factory.lua:101,106; docs/advanced.md:33-56. */
+static void grid_update(OrEnv* e) {
+  memset(e->beam, 0, sizeof(uint16_t) * e->L * e->W * e->H); /* hit sprites last one frame (A.8) */
+  draw_avatar_order(e);
+  for (int ui = 0; ui < e->n_updaters; ++ui) {
+    const Updater* u = &e->updaters[ui];
+    int avatar_comp = 0;
+    for (int p = 0; p < e->P && !avatar_comp; ++p) if (find_comp(e, &e->obj[e->avatar_obj[p]], u->comp_type)) avatar_comp = 1;
+    if (avatar_comp) {
+      for (int i = 0; i < e->P; ++i) run_updater(e, u, e->avatar_obj[e->order[i]]);
+    } else {
+      for (int oi = 0; oi < e->n_obj; ++oi) if (find_comp(e, &e->obj[oi], u->comp_type)) run_updater(e, u, oi);
+    }
+  }
+  process_queue(e);
+  e->frame++;
+}
+
+/* BaseSimulation:update -- base_simulation.lua:476-486 (preUpdate all, then update all). */
+static void simulation_update(OrEnv* e) {
+  for (int p = 0; p < e->P; ++p) e->obj[e->avatar_obj[p]].reward = 0.0; /* Avatar:preUpdate :330-332 */
+  for (int oi = 0; oi < e->n_obj; ++oi) {
+    Obj* o = &e->obj[oi];
+    const KindDef* k = kind_of(e, o);
+    for (int i = 0; i < k->n_comps; ++i) {
+      const CompDef* c = &e->comps[k->comp0 + i];
+      switch (c->type) {
+        case MPB_C_DIRT_SPAWNER: { /* clean_up/components.lua:329-340 */
+          if (e->spawner_t > c->ip[0]) {
+            uint32_t w[4]; rng(e, RS_SCENE, SCENE_DRAW_DIRT, w);
+            if (u01(w[0], w[1]) < c->dp[0]) {
+              int n = 0; /* set.toSortedList(potentialDirts): inactive dirt pieces in piece order */
+              for (int j = 0; j < e->n_obj; ++j) { const CompDef* dt = find_comp(e, &e->obj[j], MPB_C_DIRT_TRACKER); if (dt && e->obj[j].state == dt->ip[1]) ++n; }
+              if (n > 0) {
+                int kk = (int)pick(w[2], (uint32_t)n);
+                for (int j = 0; j < e->n_obj; ++j) { const CompDef* dt = find_comp(e, &e->obj[j], MPB_C_DIRT_TRACKER); if (dt && e->obj[j].state == dt->ip[1]) { if (kk-- == 0) { enqueue(e, ACT_SET_STATE, j, dt->ip[0], 0, 0); break; } } }
+              }
+            }
+          }
+          e->spawner_t++;
+        } break;
+        case MPB_C_STOCHASTIC_INTERVAL_EPISODE_ENDING: e->ending_t++; break; /* component_library.lua:946-948 */
+        case MPB_C_AVATAR: { /* Avatar:update -- avatar_library.lua:334-354 */
+          if (o->freeze == 1) o->movement_allowed = 1;
+          o->freeze = o->freeze > 0 ? o->freeze - 1 : 0;
+          if (o->removal == 1) enqueue(e, ACT_SET_STATE, oi, c->ip[2], 0, 0);
+          o->removal = o->removal > 0 ? o->removal - 1 : 0;
+        } break;
+        case MPB_C_APPLE_GROW: { /* clean_up/components.lua:64-80 */
+          double dirt = (double)e->dirt_count, clean = (double)e->clean_count;
+          double fraction = dirt / (dirt + clean);
+          double interpolation = (fraction - c->dp[1]) / (c->dp[2] - c->dp[1]);
+          interpolation = fmin(interpolation, 1.0);
+          double probability = c->dp[0] * interpolation;
+          uint32_t w[4]; rng(e, RS_OBJECT, oi, w);
+          if (u01(w[0], w[1]) < probability) enqueue(e, ACT_SET_STATE, oi, c->ip[0], 0, 0);
+        } break;
+        default: break;
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Episode start: api:start (api_factory.lua:85-102), BaseSimulation:start/_avatarStart
+ * (base_simulation.lua:396-471).
+ * ---------------------------------------------------------------------------------------- */
+static void episode_start(OrEnv* e) {
+  int cells = e->W * e->H;
+  e->frame = 0; e->step = 0; e->cont = 1; e->done = 0; e->qn = e->qnn = 0; e->evn = 0;
+  memset(e->grid, 0, sizeof(int) * e->L * cells);
+  memset(e->beam, 0, sizeof(uint16_t) * e->L * cells);
+  e->dirt_count = e->clean_count = 0; e->spawner_t = 1; e->ending_t = 1; /* reset(): :271-274,:324-327, component_library.lua:942-944 */
+  memset(e->cleaned_flag, 0, sizeof e->cleaned_flag); memset(e->ate_flag, 0, sizeof e->ate_flag);
+  for (int oi = 0; oi < e->n_obj; ++oi) {
+    const int* d = &e->objdef[oi * MPB_OBJ_COLS];
+    Obj* o = &e->obj[oi];
+    memset(o, 0, sizeof *o);
+    o->kind = d[MPB_OBJ_KIND]; o->x = d[MPB_OBJ_X]; o->y = d[MPB_OBJ_Y]; o->orient = d[MPB_OBJ_ORIENT];
+    o->state = d[MPB_OBJ_STATE]; o->prev_state = -1; o->layer = -1; o->state_frame = 0; o->movement_allowed = 1;
+    if (!kind_of(e, o)->is_avatar) { /* Transform:start -> createPiece (component_library.lua:236-254) */
+      o->layer = state_def(e, o, o->state)->layer;
+      place(e, oi);
+    }
+  }
+  /* _avatarStart: groupShuffledWithCount per spawn group, sampled without replacement. */
+  for (int g = 0; g < e->n_groups; ++g) {
+    int members[1024], n = 0, k = 0;
+    for (int p = 0; p < e->P; ++p) if (find_comp(e, &e->obj[e->avatar_obj[p]], MPB_C_AVATAR)->ip[3] == g) ++k;
+    if (k == 0) continue;
+    for (int i = 0; i < e->n_obj && n < 1024; ++i) { const Obj* c = &e->obj[i]; if (c->layer >= 0 && (state_def(e, c, c->state)->groups & (1u << g))) members[n++] = i; }
+    int j = 0;
+    for (int p = 0; p < e->P; ++p) {
+      int oi = e->avatar_obj[p]; Obj* o = &e->obj[oi];
+      const CompDef* av = find_comp(e, o, MPB_C_AVATAR);
+      if (av->ip[3] != g) continue;
+      uint32_t w[4]; rng(e, RS_AVATAR_RESET, p, w);
+      int r = j + (int)pick(w[0], (uint32_t)(n - j)); /* partial Fisher-Yates */
+      int t = members[j]; members[j] = members[r]; members[r] = t;
+      o->x = e->obj[members[j]].x; o->y = e->obj[members[j]].y;
+      o->orient = av->ip[10] ? (int)(w[1] & 3u) : 0;          /* Avatar:start :299-304 */
+      o->layer = state_def(e, o, o->state)->layer;
+      place(e, oi);
+      o->spawn_group = av->ip[4] >= 0 ? av->ip[4] : av->ip[3]; /* Avatar:postStart :322-328 */
+      for (int a = 0; a < 4; ++a) o->act[a] = 0;
+      ++j;
+    }
+  }
+  /* postStart on all objects. */
+  for (int oi = 0; oi < e->n_obj; ++oi) {
+    Obj* o = &e->obj[oi];
+    const KindDef* k = kind_of(e, o);
+    for (int i = 0; i < k->n_comps; ++i) {
+      const CompDef* c = &e->comps[k->comp0 + i];
+      if (c->type == MPB_C_ANIMATION && c->ip[11]) { /* component_library.lua:1064-1068 */
+        uint32_t w[4]; rng(e, RS_OBJECT_RESET, oi, w);
+        enqueue(e, ACT_SET_STATE, oi, c->ip[1 + pick(w[0], (uint32_t)c->ip[0])], 0, 0);
+      } else if (c->type == MPB_C_DIRT_TRACKER) {    /* clean_up/components.lua:103-116 */
+        if (o->state == c->ip[1]) e->clean_count++; else if (o->state == c->ip[0]) e->dirt_count++;
+      }
+    }
+  }
+  grid_update(e); /* api:start ends with one grid:update (api_factory.lua:101) */
+  e->step_type = 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Rendering: world:createView + tile.Scene:render (avatar_library.lua:225-277,
+ * base_simulation.lua:347-368). Policies A.11-A.14.
+ * ---------------------------------------------------------------------------------------- */
+static inline void blend_px(uint8_t* dst, const uint8_t* src) {
+  unsigned a = src[3];
+  if (a == 255) { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; }
+  else if (a != 0) for (int c = 0; c < 3; ++c) dst[c] = (uint8_t)((src[c] * a + dst[c] * (255u - a)) / 255u); /* A.14: truncate */
+}
+static void draw_sprite(const OrEnv* e, uint8_t* img, int stride, int px, int py, int sprite, int facing) {
+  int S = e->S;
+  const uint8_t* t = e->atlas + ((size_t)sprite * 4 + facing) * S * S * 4;
+  for (int y = 0; y < S; ++y) for (int x = 0; x < S; ++x) blend_px(img + (size_t)(py + y) * stride + (px + x) * 3, t + (y * S + x) * 4);
+}
+static void draw_cell(const OrEnv* e, uint8_t* img, int stride, int px, int py, int cell, int viewer, int viewer_orient) {
+  int cells = e->W * e->H;
+  const int* map = e->sprite_map + (size_t)viewer * e->n_sprites;
+  for (int l = 0; l < e->L; ++l) {
+    int q = e->grid[l * cells + cell] - 1;
+    if (q >= 0) {
+      const Obj* o = &e->obj[q];
+      int sp = state_def(e, o, o->state)->sprite;
+      if (sp >= 0) draw_sprite(e, img, stride, px, py, map[sp], (o->orient - viewer_orient) & 3);
+    }
+    uint16_t b = e->beam[l * cells + cell];
+    if (b) draw_sprite(e, img, stride, px, py, map[(b - 1) >> 2], (((b - 1) & 3) - viewer_orient) & 3);
+  }
+}
+void oracle_render_player(const OrEnv* e, int p, uint8_t* img) {
+  int S = e->S, vw = e->view_l + e->view_r + 1, vh = e->view_f + e->view_b + 1, stride = vw * S * 3;
+  memset(img, 0, (size_t)vh * S * stride);
+  const Obj* a = &e->obj[e->avatar_obj[p]];
+  for (int vy = 0; vy < vh; ++vy) for (int vx = 0; vx < vw; ++vx) {
+    if (a->layer < 0) { draw_sprite(e, img, stride, vx * S, vy * S, e->oov_sprite, 0); continue; } /* A.13 */
+    int r = (a->orient + 1) & 3, f = a->orient; /* A.11 */
+    int dxr = vx - e->view_l, dyf = e->view_f - vy;
+    int x = a->x + DX[r] * dxr + DX[f] * dyf, y = a->y + DY[r] * dxr + DY[f] * dyf;
+    if (!wrap_or_reject(e, &x, &y)) { draw_sprite(e, img, stride, vx * S, vy * S, e->oob_sprite, 0); continue; }
+    draw_cell(e, img, stride, vx * S, vy * S, cell_of(e, x, y), p, a->orient);
+  }
+}
+void oracle_render_world(const OrEnv* e, uint8_t* img) {
+  int S = e->S, stride = e->W * S * 3;
+  memset(img, 0, (size_t)e->H * S * stride);
+  for (int y = 0; y < e->H; ++y) for (int x = 0; x < e->W; ++x) draw_cell(e, img, stride, x * S, y * S, cell_of(e, x, y), e->P, 0);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Public C API (host pointers only).
+ * ---------------------------------------------------------------------------------------- */
+#define SEC(name) const MpbSection* s_##name = mpb_find(blob, n, #name); if (!s_##name) { fprintf(stderr, "oracle: missing section %s\n", #name); oracle_destroy(e); return 0; }
+void oracle_destroy(OrEnv* e);
+
+OrEnv* oracle_create(const void* blob, size_t n, uint64_t seed) {
+  OrEnv* e = (OrEnv*)calloc(1, sizeof(OrEnv));
+  SEC(meta) SEC(atlas) SEC(sprite_opaque) SEC(states) SEC(kinds) SEC(comps) SEC(comps_f) SEC(objects) SEC(hits) SEC(action_table) SEC(sprite_map) SEC(scalar_obs)
+  const int32_t* m = (const int32_t*)mpb_data(blob, s_meta);
+  e->W = m[MPB_META_W]; e->H = m[MPB_META_H]; e->L = m[MPB_META_L]; e->P = m[MPB_META_P]; e->S = m[MPB_META_SPRITE_SIZE];
+  e->topology = m[MPB_META_TOPOLOGY]; e->max_frames = m[MPB_META_MAX_FRAMES]; e->n_obj = m[MPB_META_N_OBJECTS];
+  e->n_kinds = m[MPB_META_N_KINDS]; e->n_sprites = m[MPB_META_N_SPRITES]; e->n_hits = m[MPB_META_N_HITS]; e->n_groups = m[MPB_META_N_GROUPS];
+  e->view_l = m[MPB_META_VIEW_LEFT]; e->view_r = m[MPB_META_VIEW_RIGHT]; e->view_f = m[MPB_META_VIEW_FORWARD]; e->view_b = m[MPB_META_VIEW_BACKWARD];
+  e->n_actions = m[MPB_META_N_ACTIONS]; e->oob_sprite = m[MPB_META_OOB_SPRITE]; e->oov_sprite = m[MPB_META_OOV_SPRITE]; e->n_scalar = m[MPB_META_N_SCALAR_OBS];
+  if (e->P > OR_MAX_PLAYERS || e->L > OR_MAX_LAYERS) { oracle_destroy(e); return 0; }
+  int n_states = m[MPB_META_N_STATES], n_comps = m[MPB_META_N_COMPS];
+  e->states = (StateDef*)calloc(n_states, sizeof(StateDef));
+  const int32_t* st = (const int32_t*)mpb_data(blob, s_states);
+  for (int i = 0; i < n_states; ++i) { e->states[i].layer = st[i * 4]; e->states[i].sprite = st[i * 4 + 1]; e->states[i].contact = st[i * 4 + 2]; e->states[i].groups = (uint32_t)st[i * 4 + 3]; }
+  e->kinds = (KindDef*)calloc(e->n_kinds, sizeof(KindDef));
+  const int32_t* kd = (const int32_t*)mpb_data(blob, s_kinds);
+  for (int i = 0; i < e->n_kinds; ++i) { e->kinds[i].state0 = kd[i * 6]; e->kinds[i].n_states = kd[i * 6 + 1]; e->kinds[i].comp0 = kd[i * 6 + 2]; e->kinds[i].n_comps = kd[i * 6 + 3]; e->kinds[i].is_avatar = kd[i * 6 + 4]; }
+  e->comps = (CompDef*)calloc(n_comps, sizeof(CompDef));
+  const int32_t* ci = (const int32_t*)mpb_data(blob, s_comps); const double* cd = (const double*)mpb_data(blob, s_comps_f);
+  for (int i = 0; i < n_comps; ++i) { e->comps[i].type = ci[i * (MPB_COMP_NI + 1)]; for (int j = 0; j < MPB_COMP_NI; ++j) e->comps[i].ip[j] = ci[i * (MPB_COMP_NI + 1) + 1 + j]; for (int j = 0; j < MPB_COMP_ND; ++j) e->comps[i].dp[j] = cd[i * MPB_COMP_ND + j]; }
+#define DUP(dst, sec, type) e->dst = (type*)malloc(s_##sec->nbytes); memcpy(e->dst, mpb_data(blob, s_##sec), s_##sec->nbytes);
+  DUP(objdef, objects, int) DUP(hits, hits, int) DUP(action_table, action_table, int) DUP(sprite_map, sprite_map, int) DUP(scalar_obs, scalar_obs, int)
+  DUP(atlas, atlas, uint8_t) DUP(sprite_opaque, sprite_opaque, uint8_t)
+  e->obj = (Obj*)calloc(e->n_obj, sizeof(Obj));
+  e->grid = (int*)calloc((size_t)e->L * e->W * e->H, sizeof(int));
+  e->beam = (uint16_t*)calloc((size_t)e->L * e->W * e->H, sizeof(uint16_t));
+  for (int oi = 0; oi < e->n_obj; ++oi) {
+    const KindDef* k = &e->kinds[e->objdef[oi * MPB_OBJ_COLS]];
+    if (!k->is_avatar) continue;
+    for (int i = 0; i < k->n_comps; ++i) if (e->comps[k->comp0 + i].type == MPB_C_AVATAR) e->avatar_obj[e->comps[k->comp0 + i].ip[0]] = oi;
+  }
+  build_updaters(e);
+  e->key[0] = (uint32_t)seed; e->key[1] = (uint32_t)(seed >> 32);
+  e->episode = -1; e->done = 1;
+  return e;
+}
+void oracle_destroy(OrEnv* e) {
+  if (!e) return;
+  free(e->states); free(e->kinds); free(e->comps); free(e->objdef); free(e->hits); free(e->action_table); free(e->sprite_map);
+  free(e->scalar_obs); free(e->atlas); free(e->sprite_opaque); free(e->obj); free(e->grid); free(e->beam); free(e->q); free(e->qnext);
+  free(e->ev); free(e->updaters); free(e);
+}
+/* Starts the next episode; returns StepType.FIRST (0). */
+int oracle_reset(OrEnv* e) { e->episode++; episode_start(e); return 0; }
+void oracle_set_episode(OrEnv* e, int episode) { e->episode = episode - 1; }
+
+/* One env step (api:advance, api_factory.lua:104-111). `actions[P]` are discrete action ids
+ * (discrete_action_wrapper.py:97-100). Returns the step type: 0 FIRST, 1 MID, 2 LAST.
+ * Policy A.17: a step after LAST ignores the action and starts a new episode. */
+int oracle_step(OrEnv* e, const int32_t* actions) {
+  if (e->done) return oracle_reset(e);
+  e->step++;
+  e->evn = 0;
+  for (int p = 0; p < e->P; ++p) { /* Avatar:discreteActions -- avatar_library.lua:218-223 */
+    int a = actions[p];
+    if (a < 0 || a >= e->n_actions) a = 0;
+    for (int f = 0; f < 4; ++f) e->obj[e->avatar_obj[p]].act[f] = e->action_table[a * 4 + f];
+  }
+  simulation_update(e);
+  grid_update(e);
+  int cont = e->cont && e->step < e->max_frames;
+  e->step_type = cont ? 1 : 2;
+  e->done = !cont;
+  return e->step_type;
+}
+
+void oracle_get_rewards(const OrEnv* e, double* out) { for (int p = 0; p < e->P; ++p) out[p] = e->step_type == 0 ? 0.0 : e->obj[e->avatar_obj[p]].reward; }
+double oracle_get_discount(const OrEnv* e) { return e->step_type == 1 ? 1.0 : 0.0; }
+int oracle_get_step_type(const OrEnv* e) { return e->step_type; }
+/* out[P][n_scalar] in the order of section "scalar_obs". */
+void oracle_get_scalar_obs(const OrEnv* e, double* out) {
+  for (int p = 0; p < e->P; ++p) {
+    const Obj* o = &e->obj[e->avatar_obj[p]];
+    for (int k = 0; k < e->n_scalar; ++k) {
+      double v = 0.0;
+      if (e->scalar_obs[k] == MPB_OBS_READY_TO_SHOOT) { /* Zapper:readyToShoot -- avatar_library.lua:737-744 */
+        const CompDef* z = find_comp(e, o, MPB_C_ZAPPER);
+        if (avatar_is_alive(e, o)) v = fmax(1.0 - (double)o->zap_cool / (double)z->ip[0], 0.0);
+      } else if (e->scalar_obs[k] == MPB_OBS_NUM_OTHERS_WHO_CLEANED) v = (double)o->num_others_cleaned;
+      out[p * e->n_scalar + k] = v;
+    }
+  }
+}
+/* out[P][4] = x, y, orientation, alive. */
+void oracle_get_avatars(const OrEnv* e, int32_t* out) {
+  for (int p = 0; p < e->P; ++p) { const Obj* o = &e->obj[e->avatar_obj[p]]; out[p * 4] = o->x; out[p * 4 + 1] = o->y; out[p * 4 + 2] = o->orient; out[p * 4 + 3] = o->layer >= 0; }
+}
+/* Sprite grid in the engine's encoding: out[L][cells] uint16 (beams merged in). */
+void oracle_get_grid(const OrEnv* e, uint16_t* out) {
+  int cells = e->W * e->H;
+  for (int l = 0; l < e->L; ++l) for (int c = 0; c < cells; ++c) {
+    int q = e->grid[l * cells + c] - 1; uint16_t v = 0;
+    if (q >= 0) { const Obj* o = &e->obj[q]; int sp = state_def(e, o, o->state)->sprite; if (sp >= 0) v = MPB_CELL(sp, o->orient); }
+    if (e->beam[l * cells + c]) v = e->beam[l * cells + c];
+    out[l * cells + c] = v;
+  }
+}
+int oracle_get_events(const OrEnv* e, int32_t* out, int max_events) {
+  int n = e->evn < max_events ? e->evn : max_events;
+  for (int i = 0; i < n; ++i) { out[i * 3] = e->ev[i].type; out[i * 3 + 1] = e->ev[i].a; out[i * 3 + 2] = e->ev[i].b; }
+  return e->evn;
+}
+int oracle_get_object_state(const OrEnv* e, int oi) { return e->obj[oi].state; }
+void oracle_get_counters(const OrEnv* e, int32_t* out) { out[0] = e->dirt_count; out[1] = e->clean_count; out[2] = e->frame; out[3] = e->step; out[4] = e->episode; }
+
+/* Test hooks: place an avatar / set an object state directly (bypassing the queue). */
+void oracle_debug_set_avatar(OrEnv* e, int p, int x, int y, int orient) {
+  int oi = e->avatar_obj[p]; Obj* o = &e->obj[oi];
+  lift(e, oi); o->x = x; o->y = y; o->orient = orient & 3;
+  if (o->layer < 0) { o->state = find_comp(e, o, MPB_C_AVATAR)->ip[1]; o->layer = state_def(e, o, o->state)->layer; }
+  place(e, oi);
+}
+void oracle_debug_set_object_state(OrEnv* e, int oi, int state) { do_set_state(e, oi, state); process_queue(e); }
+
+/* CPU baseline: `n_envs` independent envs stepped `n_steps` times with uniform-random actions
+ * (splitmix64 stream; not part of parity), rendering every observation each step like the
+ * reference does. Envs are split over `n_threads` pthreads. Returns env-steps executed. */
+static inline uint64_t splitmix64(uint64_t* s) { uint64_t z = (*s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+typedef struct { const void* blob; size_t n; int b0, b1, n_steps, render; uint64_t seed; long total; uint64_t sum; } RunArgs;
+static void* run_worker(void* argp) {
+  RunArgs* a = (RunArgs*)argp;
+  for (int b = a->b0; b < a->b1; ++b) {
+    OrEnv* e = oracle_create(a->blob, a->n, a->seed + (uint64_t)b);
+    if (!e) continue;
+    int vw = e->view_l + e->view_r + 1, vh = e->view_f + e->view_b + 1;
+    uint8_t* rgb = (uint8_t*)malloc((size_t)vw * vh * e->S * e->S * 3);
+    uint8_t* world = (uint8_t*)malloc((size_t)e->W * e->H * e->S * e->S * 3);
+    uint64_t s = a->seed * 0x2545F4914F6CDD1Dull + (uint64_t)b; int32_t act[OR_MAX_PLAYERS]; double rew[OR_MAX_PLAYERS];
+    oracle_reset(e);
+    for (int t = 0; t < a->n_steps; ++t) {
+      for (int p = 0; p < e->P; ++p) act[p] = (int32_t)(splitmix64(&s) % (uint64_t)e->n_actions);
+      oracle_step(e, act);
+      oracle_get_rewards(e, rew);
+      for (int p = 0; p < e->P; ++p) a->sum += (uint64_t)rew[p];
+      if (a->render) { for (int p = 0; p < e->P; ++p) { oracle_render_player(e, p, rgb); a->sum += rgb[1000]; } oracle_render_world(e, world); a->sum += world[5000]; }
+      ++a->total;
+    }
+    free(rgb); free(world); oracle_destroy(e);
+  }
+  return 0;
+}
+long oracle_run_random(const void* blob, size_t n, int n_envs, int n_steps, int n_threads, uint64_t seed, int render, uint64_t* checksum) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > n_envs) n_threads = n_envs;
+  pthread_t* th = (pthread_t*)calloc(n_threads, sizeof(pthread_t));
+  RunArgs* args = (RunArgs*)calloc(n_threads, sizeof(RunArgs));
+  for (int t = 0; t < n_threads; ++t) {
+    RunArgs a = {blob, n, (int)((long)n_envs * t / n_threads), (int)((long)n_envs * (t + 1) / n_threads), n_steps, render, seed, 0, 0};
+    args[t] = a;
+    pthread_create(&th[t], 0, run_worker, &args[t]);
+  }
+  long total = 0; uint64_t sum = 0;
+  for (int t = 0; t < n_threads; ++t) { pthread_join(th[t], 0); total += args[t].total; sum += args[t].sum; }
+  free(th); free(args);
+  if (checksum) *checksum = sum;
+  return total;
+}
