@@ -1,0 +1,118 @@
+/* mp_engine.h -- C ABI of the B200 batched Melting Pot substrate engine (libmpengine.so).
+ *
+ * This is the drop-in boundary for the reference's hot path. In the reference the path sits
+ * behind the pybind11 module `dmlab2d` (third-party), bound at
+ *   /root/reference/meltingpot/utils/substrates/builder.py:179-187
+ *     env_raw = dmlab2d.Lab2d(_DMLAB2D_ROOT, lab2d_settings_dict)
+ *     dmlab2d.Environment(env=env_raw, observation_names=..., seed=seed)
+ * and is consumed through Lab2dWrapper.{reset,step,observation,...}
+ *   /root/reference/meltingpot/utils/substrates/wrappers/base.py:26-84.
+ * Each entry point below names the reference call it replaces. Plain pointers and sizes only:
+ * no torch / C++ types cross this boundary. All functions return 0 on success or a negative
+ * MP_E_* code; mp_last_error() describes the most recent failure on the calling thread.
+ * Nothing here ever falls back to a CPU implementation.
+ */
+#ifndef MP_ENGINE_H_
+#define MP_ENGINE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mp_engine* mp_handle;
+
+enum {
+  MP_OK = 0,
+  MP_E_INVALID = -1,     /* bad argument / malformed blob */
+  MP_E_UNSUPPORTED = -2, /* substrate family or parameter outside what the kernels implement */
+  MP_E_CUDA = -3,        /* CUDA runtime error (message in mp_last_error) */
+  MP_E_NO_DEVICE = -4    /* no usable sm_100 device: the engine refuses to run */
+};
+
+/* Option flags for mp_create / mp_set_flags. */
+enum {
+  MP_FLAG_RENDER_WORLD = 1u << 0, /* produce WORLD.RGB (base_simulation.lua:347-362) */
+  MP_FLAG_RENDER_PLAYERS = 1u << 1, /* produce {i}.RGB (avatar_library.lua:264-276) */
+  MP_FLAG_DEFAULT = 3u
+};
+
+/* Device buffers owned by the engine; valid until mp_destroy. Contents are overwritten by the
+ * next mp_step/mp_reset on the same handle. B = num_envs, P = players. */
+typedef struct mp_buffers {
+  int32_t num_envs, num_players;
+  int32_t rgb_h, rgb_w;     /* per-player view in pixels (88 x 88 for clean_up) */
+  int32_t world_h, world_w; /* WORLD.RGB in pixels */
+  int32_t num_actions;      /* discrete actions per player */
+  int32_t num_scalar_obs;   /* per-player f64 observations besides REWARD */
+  uint8_t* rgb;             /* u8  [B][P][rgb_h][rgb_w][3]      "{i}.RGB" */
+  uint8_t* world_rgb;       /* u8  [B][world_h][world_w][3]     "WORLD.RGB" */
+  double* reward;           /* f64 [B][P]                       "{i}.REWARD" */
+  double* discount;         /* f64 [B]   0.0 on FIRST/LAST, 1.0 mid-episode */
+  int64_t* step_type;       /* i64 [B]   dm_env.StepType: 0 FIRST, 1 MID, 2 LAST */
+  double* scalar_obs;       /* f64 [num_scalar_obs][B][P], order of blob section "scalar_obs" */
+  int32_t* avatar_state;    /* i32 [B][P][4] x, y, orientation, alive (debug / parity) */
+  uint16_t* grid;           /* u16 [B][L][cells_padded] sprite grid (debug / parity) */
+  int32_t grid_layers, grid_cells, grid_cells_padded;
+} mp_buffers;
+
+/* Replaces dmlab2d.Lab2d(...) + dmlab2d.Environment(...) (builder.py:182-187) for `num_envs`
+ * independent instances on CUDA device `device`. `blob` is a compiled substrate
+ * (include/mpb_format.h). Env b uses RNG key `seed + env_index_base + b`, so results do not
+ * depend on how envs are sharded over GPUs. Does NOT start an episode; call mp_reset. */
+int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uint64_t seed,
+              uint64_t env_index_base, uint32_t flags, mp_handle* out);
+
+/* Replaces Lab2dWrapper.close (wrappers/base.py:82-84). */
+int mp_destroy(mp_handle h);
+
+int mp_set_flags(mp_handle h, uint32_t flags);
+
+/* Replaces dmlab2d.Environment.reset (wrappers/base.py:30-32; api_factory.lua:85-102): every
+ * env (or only those with env_mask[b] != 0; `env_mask` is a DEVICE pointer or NULL) starts its
+ * next episode and its FIRST observation is rendered. Asynchronous on `stream` (a cudaStream_t). */
+int mp_reset(mp_handle h, const uint8_t* env_mask, void* stream);
+
+/* Replaces dmlab2d.Environment.step (wrappers/base.py:34-36; api_factory.lua:104-111) including
+ * the DiscreteActionWrapper table lookup (discrete_action_wrapper.py:97-100).
+ * `actions` is a DEVICE pointer to int32 [B][P] discrete action ids. Envs whose previous step was
+ * LAST ignore the action and start a new episode (FIRST). Runs the state transition and renders
+ * all observations. Asynchronous on `stream`. */
+int mp_step(mp_handle h, const int32_t* actions, void* stream);
+
+/* State transition only / rendering only (mp_step == mp_step_state + mp_render). */
+int mp_step_state(mp_handle h, const int32_t* actions, void* stream);
+int mp_render(mp_handle h, void* stream);
+
+/* Replaces Lab2dWrapper.observation / *_spec (wrappers/base.py:38-80): where the outputs live. */
+int mp_get_buffers(mp_handle h, mp_buffers* out);
+
+/* Host-buffer convenience used for the end-to-end metric: copies `actions_host` (int32 [B][P],
+ * ideally pinned) to the device, steps, renders, copies the requested outputs into the given
+ * HOST buffers (any may be NULL to skip) and synchronises `stream`. */
+typedef struct mp_host_outputs {
+  uint8_t* rgb;
+  uint8_t* world_rgb;
+  double* reward;
+  double* discount;
+  int64_t* step_type;
+  double* scalar_obs;
+} mp_host_outputs;
+int mp_step_host(mp_handle h, const int32_t* actions_host, const mp_host_outputs* out, void* stream);
+int mp_reset_host(mp_handle h, const mp_host_outputs* out, void* stream);
+
+/* Number of kernels this engine has launched since creation (all streams). */
+int mp_launch_count(mp_handle h, uint64_t* out);
+
+/* Algorithmic bytes one env-step moves (SURVEY.md section 8d formula), for roofline reports. */
+int mp_algorithmic_bytes(mp_handle h, uint64_t* per_env_step, uint64_t* render_per_env_step);
+
+const char* mp_last_error(void);
+const char* mp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MP_ENGINE_H_ */

@@ -1,0 +1,124 @@
+// common.cuh -- device-side tables, per-env state layout and RNG shared by the kernels.
+//
+// Data layout in HBM (struct-of-arrays, env instance on the leading axis):
+//   grid        u16 [B][L][cells_pad]   sprite grid: 0 empty, else 1 + sprite*4 + orientation.
+//                                       This is the engine's view of "which piece is on
+//                                       (x, y, layer)"  reduced to what the
+//                                       renderer and the collision tests need.
+//   avatar      i32 [B][P][4]           x, y, orientation, alive
+//   av_timer    i32 [B][P][4]           zap cooldown, second-beam cooldown, frame of last state
+//                                       change, spare
+//   apple/dirt/water u8 [B][n_pad]      per-entity state (family specific)
+//   env         i32 [B][8]              step, episode, done, dirt count, cleaned flags, ate flags,
+//                                       beam-dirty, spare
+// cells_pad keeps every layer row 16-byte aligned so rows can be moved with 128-bit accesses.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MP_MAX_PLAYERS 16
+#define MP_MAX_LAYERS 16
+#define MP_MAX_BEAM_CELLS 32
+#define MP_FULL 0xffffffffu
+
+enum { ENV_STEP = 0, ENV_EPISODE = 1, ENV_DONE = 2, ENV_DIRT = 3, ENV_CLEANED = 4, ENV_ATE = 5, ENV_BEAM = 6, ENV_COLS = 8 };
+enum { AV_X = 0, AV_Y = 1, AV_ORIENT = 2, AV_ALIVE = 3 };
+enum { TM_ZAP = 0, TM_BEAM2 = 1, TM_FRAME = 2 };
+// RNG streams: must match oracle/mp_oracle.c (the RNG addressing is part of the engine policy).
+enum { RS_SCENE = 0, RS_AVATAR = 1, RS_OBJECT = 2, RS_AVATAR_RESET = 3, RS_OBJECT_RESET = 4 };
+enum { SCENE_DRAW_DIRT = 0, SCENE_DRAW_EPISODE_END = 1 };
+
+struct BeamGeom {  // one beam footprint, cells in visiting order (policy A.8)
+  int n;
+  int depth;
+  int8_t lat[MP_MAX_BEAM_CELLS];     // lateral offset, negative = left of the shooter
+  int8_t fwd[MP_MAX_BEAM_CELLS];     // forward distance
+  int8_t parent[MP_MAX_BEAM_CELLS];  // cell that must be visited and unblocked first, or -1
+};
+
+struct Tables {
+  // geometry
+  int W, H, cells, cells_pad, L, P, topology, max_frames;
+  int view_l, view_r, view_f, view_b, n_sprites, oob_sprite, oov_sprite, n_actions, n_scalar;
+  int scalar_obs[4];
+  // shared avatar machinery
+  int avatar_layer, n_spawn;
+  int avatar_sprite[MP_MAX_PLAYERS];
+  int zap_cooldown, zap_respawn, zap_remove, zap_layer, zap_sprite, zap_hit;
+  double zap_penalty, zap_reward;
+  BeamGeom zap_geom;
+  // clean_up family
+  int nA, nD, nW, nA_pad, nD_pad, nW_pad;
+  int apple_layer, apple_sprite, dirt_layer, dirt_sprite, water_layer, n_anim, anim_frames, anim_random;
+  int water_sprite[8];
+  int clean_cooldown, clean_layer, clean_sprite, clean_hit;
+  BeamGeom clean_geom;
+  int dirt_delay, end_min_frames, end_interval, taste_role, dirt_count0;
+  double grow_rate, grow_depletion, grow_restoration, eat_reward, dirt_prob, end_prob, taste_amount;
+  // device tables
+  const uint16_t* init_grid;   // [L][cells_pad]
+  const int32_t* action_table; // [n_actions][4]
+  const int32_t* apple;        // [nA][3] obj id, cell, initially live
+  const int32_t* dirt;         // [nD][3] obj id, cell, initially dirty
+  const int32_t* water;        // [nW][2] obj id, cell
+  const int32_t* spawn_cell;   // [n_spawn]
+  const uint8_t* solid;        // [cells_pad] 255 where the avatar layer is statically occupied
+  const uint8_t* cell_flags;   // [cells_pad] bit h: a BeamBlocker for hit h sits here
+  const int16_t* apple_of_cell;  // [cells_pad] apple index or -1
+  const int16_t* dirt_of_cell;   // [cells_pad] dirt index or -1
+  // render tables
+  const uint8_t* atlas;        // [n_sprites][4][2][8][16]: facing, half (px 0-3 | 4-7), row, 16 B
+  const int16_t* sprite_map;   // [P+1][n_sprites]
+  const uint8_t* sprite_opaque;  // [n_sprites] 1 = every pixel alpha 255 and never remapped
+};
+
+struct State {
+  int B;
+  uint64_t seed;  // key of env b = seed + b (env_index_base already folded in)
+  uint16_t* grid;
+  int32_t* avatar;
+  int32_t* av_timer;
+  uint8_t* apple;
+  uint8_t* dirt;
+  uint8_t* water;
+  int32_t* env;
+  // outputs
+  double* reward;
+  double* discount;
+  int64_t* step_type;
+  double* scalar_obs;  // [n_scalar][B][P]
+  uint8_t* rgb;
+  uint8_t* world_rgb;
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+__device__ __forceinline__ uint32_t pick(uint32_t w, uint32_t n) { return __umulhi(w, n); }
+
+__device__ __forceinline__ int dir_dx(int d) { return (d == 1) - (d == 3); }
+__device__ __forceinline__ int dir_dy(int d) { return (d == 2) - (d == 0); }
+__device__ __forceinline__ uint16_t cell_value(int sprite, int orient) { return (uint16_t)(1 + sprite * 4 + (orient & 3)); }
+
+// Maps (x, y) into the map; returns false if it falls outside a BOUNDED map.
+__device__ __forceinline__ bool wrap_or_reject(const Tables& T, int& x, int& y) {
+  if (T.topology == 1) {
+    x = x % T.W; if (x < 0) x += T.W;
+    y = y % T.H; if (y < 0) y += T.H;
+    return true;
+  }
+  return x >= 0 && x < T.W && y >= 0 && y < T.H;
+}

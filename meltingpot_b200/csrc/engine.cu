@@ -1,0 +1,452 @@
+// engine.cu -- host side of libmpengine.so: blob -> device tables, state allocation, launches, C ABI.
+// See include/mp_engine.h for the boundary contract. No CPU implementation of the path exists in
+// this library: without a CUDA device every entry point fails with MP_E_NO_DEVICE / MP_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mp_engine.h"
+#include "../../include/mpb_format.h"
+#include "common.cuh"
+#include "render.cuh"
+#include "step_clean_up.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) return fail(MP_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+template <typename T>
+struct Section {
+  const T* data = nullptr;
+  std::vector<uint32_t> shape;
+  size_t count = 0;
+};
+
+template <typename T>
+bool get_section(const void* blob, size_t n, const char* name, int dtype, Section<T>* out) {
+  const MpbSection* s = mpb_find(blob, n, name);
+  if (!s || (int)s->dtype != dtype) return false;
+  out->data = static_cast<const T*>(mpb_data(blob, s));
+  out->shape.assign(s->shape, s->shape + s->ndim);
+  out->count = s->nbytes / sizeof(T);
+  return true;
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// Beam footprint in visiting order (policy A.8): centre ray, then for each side the lateral cells
+// outwards, each followed by its forward ray of length `length - k`.
+bool make_beam_geom(int length, int radius, BeamGeom* g) {
+  std::vector<int> lat, fwd, parent;
+  int prev = -1;
+  for (int i = 1; i <= length; ++i) { lat.push_back(0); fwd.push_back(i); parent.push_back(prev); prev = (int)lat.size() - 1; }
+  for (int side = 0; side < 2; ++side) {
+    int sign = side == 0 ? -1 : 1;
+    int prev_lat = -1;
+    for (int k = 1; k <= radius; ++k) {
+      lat.push_back(sign * k); fwd.push_back(0); parent.push_back(prev_lat);
+      prev_lat = (int)lat.size() - 1;
+      int pf = prev_lat;
+      for (int i = 1; i <= length - k; ++i) { lat.push_back(sign * k); fwd.push_back(i); parent.push_back(pf); pf = (int)lat.size() - 1; }
+    }
+  }
+  if (lat.size() > MP_MAX_BEAM_CELLS) return false;
+  g->n = (int)lat.size();
+  g->depth = length + radius;
+  for (int i = 0; i < g->n; ++i) { g->lat[i] = (int8_t)lat[i]; g->fwd[i] = (int8_t)fwd[i]; g->parent[i] = (int8_t)parent[i]; }
+  return true;
+}
+
+}  // namespace
+
+struct mp_engine {
+  int device = 0;
+  int B = 0;
+  uint32_t flags = MP_FLAG_DEFAULT;
+  int family = 0;
+  Tables T{};
+  State S{};
+  RenderPlan R{};
+  mp_buffers buffers{};
+  std::vector<void*> allocs;
+  int32_t* d_actions = nullptr;  // staging for mp_step_host
+  int32_t* d_avatar_dbg = nullptr;
+  uint64_t launches = 0;
+  int sm_count = 0;
+  size_t step_smem = 0;
+  uint64_t algo_bytes = 0, render_bytes = 0;
+
+  template <typename T>
+  int upload(const std::vector<T>& host, const T** out) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(host.size() * sizeof(T), 16);
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    allocs.push_back(p);
+    CUDA_TRY(cudaMemset(p, 0, bytes));
+    if (!host.empty()) CUDA_TRY(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = static_cast<const T*>(p);
+    return MP_OK;
+  }
+  template <typename T>
+  int alloc(size_t count, T** out) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    allocs.push_back(p);
+    CUDA_TRY(cudaMemset(p, 0, bytes));
+    *out = static_cast<T*>(p);
+    return MP_OK;
+  }
+};
+
+namespace {
+
+int build_tables(mp_engine* E, const void* blob, size_t n) {
+  Section<int32_t> meta, states, kinds, comps, objects, hits, action_table, sprite_map, scalar_obs, av_table;
+  Section<double> comps_f;
+  Section<uint8_t> atlas, sprite_opaque, cell_flags;
+  Section<uint16_t> init_grid;
+  if (!get_section(blob, n, "meta", MPB_I32, &meta) || meta.count < MPB_META_COUNT) return fail(MP_E_INVALID, "blob: missing/invalid 'meta' (not an MPB%u blob?)", MPB_VERSION);
+#define NEED(sec, dt) if (!get_section(blob, n, #sec, dt, &sec)) return fail(MP_E_INVALID, "blob: missing section '%s'", #sec);
+  NEED(states, MPB_I32) NEED(kinds, MPB_I32) NEED(comps, MPB_I32) NEED(comps_f, MPB_F64) NEED(objects, MPB_I32) NEED(hits, MPB_I32)
+  NEED(action_table, MPB_I32) NEED(sprite_map, MPB_I32) NEED(scalar_obs, MPB_I32) NEED(av_table, MPB_I32)
+  NEED(atlas, MPB_U8) NEED(sprite_opaque, MPB_U8) NEED(cell_flags, MPB_U8) NEED(init_grid, MPB_U16)
+  const int32_t* m = meta.data;
+  Tables& T = E->T;
+  E->family = m[MPB_META_FAMILY];
+  T.W = m[MPB_META_W]; T.H = m[MPB_META_H]; T.cells = T.W * T.H; T.cells_pad = round_up(T.cells, 8);
+  T.L = m[MPB_META_L]; T.P = m[MPB_META_P]; T.topology = m[MPB_META_TOPOLOGY]; T.max_frames = m[MPB_META_MAX_FRAMES];
+  T.view_l = m[MPB_META_VIEW_LEFT]; T.view_r = m[MPB_META_VIEW_RIGHT]; T.view_f = m[MPB_META_VIEW_FORWARD]; T.view_b = m[MPB_META_VIEW_BACKWARD];
+  T.n_sprites = m[MPB_META_N_SPRITES]; T.oob_sprite = m[MPB_META_OOB_SPRITE]; T.oov_sprite = m[MPB_META_OOV_SPRITE];
+  T.n_actions = m[MPB_META_N_ACTIONS]; T.n_scalar = m[MPB_META_N_SCALAR_OBS];
+  if (m[MPB_META_SPRITE_SIZE] != 8) return fail(MP_E_UNSUPPORTED, "spriteSize %d (kernels are written for 8x8 sprites)", m[MPB_META_SPRITE_SIZE]);
+  if (T.P < 1 || T.P > MP_MAX_PLAYERS) return fail(MP_E_UNSUPPORTED, "%d players (max %d)", T.P, MP_MAX_PLAYERS);
+  if (T.L > MP_MAX_LAYERS) return fail(MP_E_UNSUPPORTED, "%d layers (max %d)", T.L, MP_MAX_LAYERS);
+  if (T.n_sprites > 256) return fail(MP_E_UNSUPPORTED, "%d sprites (max 256)", T.n_sprites);
+  if (T.n_scalar > 4) return fail(MP_E_UNSUPPORTED, "%d scalar observations (max 4)", T.n_scalar);
+  if (T.n_actions < 1) return fail(MP_E_INVALID, "blob has no action table (compile with the substrate config)");
+  if (T.cells >= 4096) return fail(MP_E_UNSUPPORTED, "map of %d cells (max 4095)", T.cells);
+  for (int k = 0; k < T.n_scalar; ++k) T.scalar_obs[k] = scalar_obs.data[k];
+  if (E->family != MPB_FAMILY_CLEAN_UP) return fail(MP_E_UNSUPPORTED, "substrate family %d has no CUDA state-transition kernel yet", E->family);
+
+  // ---- avatars ---------------------------------------------------------------------------------
+  T.avatar_layer = av_table.data[2];
+  int spawn_group = av_table.data[3];
+  for (int p = 0; p < T.P; ++p) {
+    const int32_t* a = av_table.data + p * 8;
+    T.avatar_sprite[p] = a[1];
+    if (a[2] != T.avatar_layer || a[3] != spawn_group || a[4] != -1) return fail(MP_E_UNSUPPORTED, "per-avatar layers / spawn groups");
+  }
+  char name[64];
+  snprintf(name, sizeof name, "spawn_cells_%d", spawn_group);
+  Section<int32_t> spawn;
+  if (!get_section(blob, n, name, MPB_I32, &spawn)) return fail(MP_E_INVALID, "blob: missing section '%s'", name);
+  T.n_spawn = (int)spawn.count;
+  if (T.n_spawn < T.P || T.n_spawn > 64) return fail(MP_E_UNSUPPORTED, "%d spawn points for %d players (need P..64)", T.n_spawn, T.P);
+
+  // ---- clean_up family tables ------------------------------------------------------------------
+  Section<int32_t> cu_ip, cu_apple, cu_dirt, cu_water, cu_water_sprites;
+  Section<double> cu_dp;
+  NEED(cu_ip, MPB_I32) NEED(cu_dp, MPB_F64) NEED(cu_apple, MPB_I32) NEED(cu_dirt, MPB_I32) NEED(cu_water, MPB_I32) NEED(cu_water_sprites, MPB_I32)
+#undef NEED
+  const int32_t* ip = cu_ip.data; const double* dp = cu_dp.data;
+  T.nA = ip[0]; T.nD = ip[1]; T.nW = ip[2];
+  T.nA_pad = round_up(std::max(T.nA, 1), 16); T.nD_pad = round_up(std::max(T.nD, 1), 16); T.nW_pad = round_up(std::max(T.nW, 1), 16);
+  T.apple_layer = ip[3]; T.apple_sprite = ip[4]; T.dirt_layer = ip[5]; T.dirt_sprite = ip[6];
+  T.water_layer = ip[8]; T.n_anim = ip[9]; T.anim_frames = ip[10]; T.anim_random = ip[11];
+  if (T.n_anim < 1 || T.n_anim > 8 || T.anim_frames < 1) return fail(MP_E_UNSUPPORTED, "animation with %d states / %d frames", T.n_anim, T.anim_frames);
+  for (int i = 0; i < T.n_anim; ++i) T.water_sprite[i] = cu_water_sprites.data[i];
+  T.zap_cooldown = ip[12]; T.zap_respawn = ip[15]; T.zap_remove = ip[16];
+  T.clean_cooldown = ip[18];
+  T.zap_layer = ip[21]; T.zap_sprite = ip[22]; T.clean_layer = ip[23]; T.clean_sprite = ip[24];
+  T.zap_hit = 0; T.clean_hit = 1;
+  for (int h = 0; h < (int)hits.count / 2; ++h) {
+    if (hits.data[h * 2] == T.zap_layer) T.zap_hit = h;
+    if (hits.data[h * 2] == T.clean_layer) T.clean_hit = h;
+  }
+  if (T.zap_cooldown <= 0 || T.clean_cooldown < 0) return fail(MP_E_UNSUPPORTED, "non-positive beam cooldowns");
+  if (!make_beam_geom(ip[13], ip[14], &T.zap_geom) || !make_beam_geom(ip[19], ip[20], &T.clean_geom))
+    return fail(MP_E_UNSUPPORTED, "beam footprint larger than %d cells", MP_MAX_BEAM_CELLS);
+  T.dirt_delay = ip[25]; T.end_min_frames = ip[26]; T.end_interval = ip[27]; T.taste_role = ip[28];
+  if (T.taste_role != 0) return fail(MP_E_UNSUPPORTED, "Taste roles other than 'free'");
+  if (T.end_interval < 1) return fail(MP_E_INVALID, "episode interval < 1");
+  T.grow_rate = dp[0]; T.grow_depletion = dp[1]; T.grow_restoration = dp[2]; T.eat_reward = dp[3];
+  T.zap_penalty = dp[4]; T.zap_reward = dp[5]; T.dirt_prob = dp[6]; T.end_prob = dp[7]; T.taste_amount = dp[8];
+
+  // ---- device copies -----------------------------------------------------------------------------
+  int rc;
+  std::vector<uint16_t> grid0((size_t)T.L * T.cells_pad, 0);
+  for (int l = 0; l < T.L; ++l) memcpy(&grid0[(size_t)l * T.cells_pad], init_grid.data + (size_t)l * T.cells, T.cells * sizeof(uint16_t));
+  if ((rc = E->upload(grid0, &T.init_grid))) return rc;
+  std::vector<int32_t> act(action_table.data, action_table.data + action_table.count);
+  if ((rc = E->upload(act, &T.action_table))) return rc;
+  std::vector<int32_t> v_apple(cu_apple.data, cu_apple.data + cu_apple.count), v_dirt(cu_dirt.data, cu_dirt.data + cu_dirt.count),
+      v_water(cu_water.data, cu_water.data + cu_water.count), v_spawn(spawn.data, spawn.data + spawn.count);
+  if ((rc = E->upload(v_apple, &T.apple)) || (rc = E->upload(v_dirt, &T.dirt)) || (rc = E->upload(v_water, &T.water)) || (rc = E->upload(v_spawn, &T.spawn_cell))) return rc;
+  std::vector<uint8_t> solid(T.cells_pad, 0), flags(T.cells_pad, 0);
+  for (int o = 0; o < m[MPB_META_N_OBJECTS]; ++o) {  // non-avatar pieces that start on the avatar layer
+    const int32_t* od = objects.data + o * MPB_OBJ_COLS;
+    const int32_t* kd = kinds.data + od[MPB_OBJ_KIND] * MPB_KIND_COLS;
+    if (kd[MPB_KIND_IS_AVATAR]) continue;
+    const int32_t* st = states.data + (kd[MPB_KIND_STATE0] + od[MPB_OBJ_STATE]) * MPB_STATE_COLS;
+    if (st[MPB_STATE_LAYER] == T.avatar_layer) solid[od[MPB_OBJ_Y] * T.W + od[MPB_OBJ_X]] = 255;
+  }
+  memcpy(flags.data(), cell_flags.data, std::min<size_t>(cell_flags.count, T.cells));
+  if ((rc = E->upload(solid, &T.solid)) || (rc = E->upload(flags, &T.cell_flags))) return rc;
+  std::vector<int16_t> apple_of(T.cells_pad, -1), dirt_of(T.cells_pad, -1);
+  T.dirt_count0 = 0;
+  for (int k = 0; k < T.nA; ++k) apple_of[v_apple[k * 3 + 1]] = (int16_t)k;
+  for (int j = 0; j < T.nD; ++j) { dirt_of[v_dirt[j * 3 + 1]] = (int16_t)j; T.dirt_count0 += v_dirt[j * 3 + 2]; }
+  if ((rc = E->upload(apple_of, &T.apple_of_cell)) || (rc = E->upload(dirt_of, &T.dirt_of_cell))) return rc;
+
+  // render tables: atlas re-laid out as [sprite][facing][half][row][16 B] so that the 8 rows of one
+  // half are 128 contiguous bytes (conflict-free 128-bit shared loads).
+  if (atlas.count != (size_t)T.n_sprites * 1024) return fail(MP_E_INVALID, "atlas has %zu bytes, expected %d", atlas.count, T.n_sprites * 1024);
+  std::vector<uint8_t> at(atlas.count);
+  for (int s = 0; s < T.n_sprites * 4; ++s)
+    for (int row = 0; row < 8; ++row)
+      for (int half = 0; half < 2; ++half)
+        memcpy(&at[(size_t)s * 256 + half * 128 + row * 16], atlas.data + (size_t)s * 256 + row * 32 + half * 16, 16);
+  if ((rc = E->upload(at, &T.atlas))) return rc;
+  std::vector<int16_t> smap((size_t)(T.P + 1) * T.n_sprites);
+  std::vector<uint8_t> opq(T.n_sprites);
+  for (int s = 0; s < T.n_sprites; ++s) opq[s] = sprite_opaque.data[s];
+  for (int v = 0; v <= T.P; ++v)
+    for (int s = 0; s < T.n_sprites; ++s) {
+      int to = sprite_map.data[(size_t)v * T.n_sprites + s];
+      smap[(size_t)v * T.n_sprites + s] = (int16_t)to;
+      if (to != s) opq[s] = 0;  // a remapped sprite must not cut the layer walk short
+    }
+  if ((rc = E->upload(smap, &T.sprite_map)) || (rc = E->upload(opq, &T.sprite_opaque))) return rc;
+  return MP_OK;
+}
+
+int build_plan(mp_engine* E) {
+  const Tables& T = E->T;
+  RenderPlan& R = E->R;
+  R.view_w = T.view_l + T.view_r + 1; R.view_h = T.view_f + T.view_b + 1;
+  R.player_bytes = R.view_w * R.view_h * 192;
+  const int cell_row_bytes = T.W * 192;
+  R.band_rows = std::max(1, R.player_bytes / cell_row_bytes);
+  R.n_bands = (T.H + R.band_rows - 1) / R.band_rows;
+  R.world_bytes = T.H * cell_row_bytes;
+  R.tile_bytes = round_up(std::max(R.player_bytes, R.band_rows * cell_row_bytes), 128);
+  R.grid_bytes = T.L * T.cells_pad * 2;
+  R.atlas_bytes = T.n_sprites * 1024;
+  R.magic_view_w = (65536u + R.view_w - 1) / R.view_w;
+  R.magic_world_w = (65536u + T.W - 1) / T.W;
+  int off = 128;  // mbarriers
+  R.off_atlas = off; off += round_up(R.atlas_bytes, 128);
+  R.off_grid0 = off; off += round_up(R.grid_bytes, 128);
+  R.off_grid1 = off; off += round_up(R.grid_bytes, 128);
+  R.off_mask = off; off += round_up(T.cells_pad * 2, 128);
+  R.off_map = off; off += round_up((T.P + 1) * T.n_sprites * 2, 128);
+  R.off_tile0 = off; off += R.tile_bytes;
+  R.off_tile1 = off; off += R.tile_bytes;
+  R.smem_bytes = off;
+  if (R.smem_bytes > 227 * 1024) return fail(MP_E_UNSUPPORTED, "render kernel needs %d B of shared memory (> 227 KB)", R.smem_bytes);
+  return MP_OK;
+}
+
+int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int mode, cudaStream_t st) {
+  const int blocks = (E->B + 3) / 4;
+  k_step_clean_up<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
+  ++E->launches;
+  CUDA_TRY(cudaGetLastError());
+  return MP_OK;
+}
+
+int launch_render(mp_engine* E, cudaStream_t st) {
+  if (!(E->flags & (MP_FLAG_RENDER_WORLD | MP_FLAG_RENDER_PLAYERS))) return MP_OK;
+  const int blocks = std::min(E->B, E->sm_count * 2);
+  k_render<<<blocks, RENDER_THREADS, E->R.smem_bytes, st>>>(E->T, E->S, E->R, E->flags);
+  ++E->launches;
+  CUDA_TRY(cudaGetLastError());
+  return MP_OK;
+}
+
+int copy_out(mp_engine* E, const mp_host_outputs* out, cudaStream_t st) {
+  if (!out) return MP_OK;
+  const mp_buffers& bf = E->buffers;
+  const size_t B = E->B, P = E->T.P;
+  if (out->rgb) CUDA_TRY(cudaMemcpyAsync(out->rgb, bf.rgb, B * P * E->R.player_bytes, cudaMemcpyDeviceToHost, st));
+  if (out->world_rgb) CUDA_TRY(cudaMemcpyAsync(out->world_rgb, bf.world_rgb, B * E->R.world_bytes, cudaMemcpyDeviceToHost, st));
+  if (out->reward) CUDA_TRY(cudaMemcpyAsync(out->reward, bf.reward, B * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (out->discount) CUDA_TRY(cudaMemcpyAsync(out->discount, bf.discount, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (out->step_type) CUDA_TRY(cudaMemcpyAsync(out->step_type, bf.step_type, B * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  if (out->scalar_obs && E->T.n_scalar) CUDA_TRY(cudaMemcpyAsync(out->scalar_obs, bf.scalar_obs, (size_t)E->T.n_scalar * B * P * sizeof(double), cudaMemcpyDeviceToHost, st));
+  return MP_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* mp_last_error(void) { return g_error.c_str(); }
+const char* mp_version(void) { return "meltingpot_b200 engine 0.1 (sm_100a)"; }
+
+int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uint64_t seed, uint64_t env_index_base, uint32_t flags, mp_handle* out) {
+  if (!blob || !out || num_envs < 1) return fail(MP_E_INVALID, "mp_create: bad arguments");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) return fail(MP_E_NO_DEVICE, "no CUDA device available (%s); this engine has no CPU path", cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return fail(MP_E_INVALID, "device %d out of range (0..%d)", device, n_dev - 1);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(MP_E_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+  DeviceGuard guard(device);
+  mp_engine* E = new mp_engine();
+  E->device = device; E->B = num_envs; E->flags = flags; E->sm_count = prop.multiProcessorCount;
+  int rc = build_tables(E, blob, blob_bytes);
+  if (rc == MP_OK) rc = build_plan(E);
+  if (rc != MP_OK) { mp_destroy(E); return rc; }
+  const Tables& T = E->T;
+  State& S = E->S;
+  S.B = num_envs; S.seed = seed + env_index_base;
+  const size_t B = num_envs, P = T.P;
+  if ((rc = E->alloc(B * T.L * T.cells_pad, &S.grid)) || (rc = E->alloc(B * P * 4, &S.avatar)) || (rc = E->alloc(B * P * 4, &S.av_timer)) ||
+      (rc = E->alloc(B * T.nA_pad, &S.apple)) || (rc = E->alloc(B * T.nD_pad, &S.dirt)) || (rc = E->alloc(B * T.nW_pad, &S.water)) ||
+      (rc = E->alloc(B * ENV_COLS, &S.env)) || (rc = E->alloc(B * P, &S.reward)) || (rc = E->alloc(B, &S.discount)) ||
+      (rc = E->alloc(B, &S.step_type)) || (rc = E->alloc(std::max<size_t>(1, T.n_scalar) * B * P, &S.scalar_obs)) ||
+      (rc = E->alloc(B * P * E->R.player_bytes, &S.rgb)) || (rc = E->alloc(B * (size_t)E->R.world_bytes, &S.world_rgb)) ||
+      (rc = E->alloc(B * P, &E->d_actions))) {
+    mp_destroy(E);
+    return rc;
+  }
+  // episode counter starts at -1 so that the first reset plays episode 0; envs start "done".
+  {
+    std::vector<int32_t> env0(B * ENV_COLS, 0);
+    for (size_t b = 0; b < B; ++b) { env0[b * ENV_COLS + ENV_EPISODE] = -1; env0[b * ENV_COLS + ENV_DONE] = 1; }
+    cudaError_t ce = cudaMemcpy(S.env, env0.data(), env0.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { mp_destroy(E); return fail(MP_E_CUDA, "cudaMemcpy(env) failed: %s", cudaGetErrorString(ce)); }
+  }
+  E->step_smem = warp_scratch_bytes(T);
+  cudaError_t ce = cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, E->R.smem_bytes);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_clean_up, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
+  if (ce != cudaSuccess) { mp_destroy(E); return fail(MP_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)); }
+  mp_buffers& bf = E->buffers;
+  bf.num_envs = num_envs; bf.num_players = T.P; bf.rgb_h = E->R.view_h * 8; bf.rgb_w = E->R.view_w * 8;
+  bf.world_h = T.H * 8; bf.world_w = T.W * 8; bf.num_actions = T.n_actions; bf.num_scalar_obs = T.n_scalar;
+  bf.rgb = S.rgb; bf.world_rgb = S.world_rgb; bf.reward = S.reward; bf.discount = S.discount; bf.step_type = S.step_type;
+  bf.scalar_obs = S.scalar_obs; bf.avatar_state = S.avatar; bf.grid = S.grid;
+  bf.grid_layers = T.L; bf.grid_cells = T.cells; bf.grid_cells_padded = T.cells_pad;
+  // observations + scalars + actions + one read and one write of the compact grid.
+  E->render_bytes = (uint64_t)P * E->R.player_bytes + (uint64_t)E->R.world_bytes + (uint64_t)T.L * T.cells * 2;
+  E->algo_bytes = (uint64_t)P * E->R.player_bytes + (uint64_t)E->R.world_bytes + 8ull * ((1 + T.n_scalar) * P + 2) + 8ull * P + 2ull * T.L * T.cells * 2;
+  *out = E;
+  return MP_OK;
+}
+
+int mp_destroy(mp_handle h) {
+  if (!h) return MP_OK;
+  {
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->allocs) cudaFree(p);
+  }
+  delete h;
+  return MP_OK;
+}
+
+int mp_set_flags(mp_handle h, uint32_t flags) {
+  if (!h) return fail(MP_E_INVALID, "null handle");
+  h->flags = flags;
+  return MP_OK;
+}
+
+int mp_reset(mp_handle h, const uint8_t* env_mask, void* stream) {
+  if (!h) return fail(MP_E_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  int rc = launch_state(h, nullptr, env_mask, 1, (cudaStream_t)stream);
+  return rc ? rc : launch_render(h, (cudaStream_t)stream);
+}
+
+int mp_step_state(mp_handle h, const int32_t* actions, void* stream) {
+  if (!h || !actions) return fail(MP_E_INVALID, "mp_step_state: null handle or actions");
+  DeviceGuard guard(h->device);
+  return launch_state(h, actions, nullptr, 0, (cudaStream_t)stream);
+}
+
+int mp_render(mp_handle h, void* stream) {
+  if (!h) return fail(MP_E_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  return launch_render(h, (cudaStream_t)stream);
+}
+
+int mp_step(mp_handle h, const int32_t* actions, void* stream) {
+  int rc = mp_step_state(h, actions, stream);
+  return rc ? rc : mp_render(h, stream);
+}
+
+int mp_get_buffers(mp_handle h, mp_buffers* out) {
+  if (!h || !out) return fail(MP_E_INVALID, "null argument");
+  *out = h->buffers;
+  return MP_OK;
+}
+
+int mp_step_host(mp_handle h, const int32_t* actions_host, const mp_host_outputs* out, void* stream) {
+  if (!h || !actions_host) return fail(MP_E_INVALID, "mp_step_host: null handle or actions");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)h->B * h->T.P * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  int rc = launch_state(h, h->d_actions, nullptr, 0, st);
+  if (!rc) rc = launch_render(h, st);
+  if (!rc) rc = copy_out(h, out, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return MP_OK;
+}
+
+int mp_reset_host(mp_handle h, const mp_host_outputs* out, void* stream) {
+  if (!h) return fail(MP_E_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_state(h, nullptr, nullptr, 1, st);
+  if (!rc) rc = launch_render(h, st);
+  if (!rc) rc = copy_out(h, out, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return MP_OK;
+}
+
+int mp_launch_count(mp_handle h, uint64_t* out) {
+  if (!h || !out) return fail(MP_E_INVALID, "null argument");
+  *out = h->launches;
+  return MP_OK;
+}
+
+int mp_algorithmic_bytes(mp_handle h, uint64_t* per_env_step, uint64_t* render_per_env_step) {
+  if (!h) return fail(MP_E_INVALID, "null handle");
+  if (per_env_step) *per_env_step = h->algo_bytes;
+  if (render_per_env_step) *render_per_env_step = h->render_bytes;
+  return MP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+// render.cuh -- sprite compositing of {i}.RGB and WORLD.RGB for every env instance.
+//
+// Restates world:createView + tile.Scene:render as used by
+//   Avatar:addObservations          /root/reference/meltingpot/lua/modules/avatar_library.lua:225-277
+//   BaseSimulation:addObservations  /root/reference/meltingpot/lua/modules/base_simulation.lua:347-368
+// (policies A.11-A.14 of the ledger: view window, sprite facing, out-of-bounds / out-of-view
+// sprites, bottom-to-top alpha compositing in render order).
+//
+// HBM-bound: per env-step it reads the 11 KB sprite grid and writes P*88*88*3 + H*W*192 bytes.
+// One persistent CTA renders whole envs: the sprite atlas is TMA-bulk-copied to shared memory once
+// per CTA, each env's grid is bulk-prefetched (double buffered) behind an mbarrier, images are
+// composed tile by tile in shared memory and leave through cp.async.bulk shared->global stores, so
+// every byte of the observations is written exactly once, fully coalesced, by the copy engine.
+#pragma once
+
+#include "common.cuh"
+#include <cstdio>
+
+struct RenderPlan {  // host-computed constants of the tiling
+  int view_w, view_h;        // cells
+  int player_bytes;          // per-player image
+  int band_rows, n_bands;    // WORLD.RGB is cut into bands of `band_rows` cell rows
+  int world_bytes;
+  int tile_bytes;            // shared-memory tile buffer (>= player_bytes, >= band bytes)
+  int grid_bytes;            // L * cells_pad * 2
+  int atlas_bytes;
+  uint32_t magic_view_w, magic_world_w;  // q = (c * magic) >> 16 == c / w for c < 4096
+  // shared memory offsets
+  int off_atlas, off_grid0, off_grid1, off_mask, off_map, off_tile0, off_tile1, smem_bytes;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (UBLKCP in SASS).
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// TMA bulk copy shared -> global.
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// dst, src: R | G<<8 | B<<16 (| A<<24 for src). Integer "over": (s*a + d*(255-a)) / 255, truncated.
+__device__ __forceinline__ uint32_t blend_px(uint32_t dst, uint32_t src) {
+  const uint32_t a = src >> 24;
+  if (a == 255u) return src;
+  if (a == 0u) return dst;
+  const uint32_t ia = 255u - a;
+  uint32_t rb = (src & 0x00FF00FFu) * a + (dst & 0x00FF00FFu) * ia;  // two 16-bit lanes, each <= 65025
+  uint32_t g = ((src >> 8) & 0xFFu) * a + ((dst >> 8) & 0xFFu) * ia;
+  rb += 0x00010001u; rb += (rb >> 8) & 0x00FF00FFu; rb = (rb >> 8) & 0x00FF00FFu;  // floor(t / 255) per lane
+  g += 1u; g += g >> 8; g = (g >> 8) & 0xFFu;
+  return rb | (g << 8);
+}
+
+// Composites pixel row `py` of the cell stack at `cell` (bits of `mask` = layers to draw, bottom
+// up) into px[8].
+__device__ __forceinline__ void compose_row(uint32_t px[8], const uint8_t* __restrict__ s_atlas, const uint16_t* __restrict__ s_grid,
+                                            const int16_t* __restrict__ s_map, const uint8_t* __restrict__ opaque, int cells_pad,
+                                            int cell, uint32_t mask, int viewer_orient, int py) {
+  while (mask) {
+    const int l = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int v = (int)s_grid[l * cells_pad + cell] - 1;
+    const int sprite = s_map[v >> 2];
+    const int facing = ((v & 3) - viewer_orient) & 3;
+    const uint8_t* t = s_atlas + (sprite * 4 + facing) * 256 + py * 16;
+    const uint4 lo = *reinterpret_cast<const uint4*>(t);
+    const uint4 hi = *reinterpret_cast<const uint4*>(t + 128);
+    if (opaque[sprite]) {
+      px[0] = lo.x; px[1] = lo.y; px[2] = lo.z; px[3] = lo.w; px[4] = hi.x; px[5] = hi.y; px[6] = hi.z; px[7] = hi.w;
+    } else {
+      px[0] = blend_px(px[0], lo.x); px[1] = blend_px(px[1], lo.y); px[2] = blend_px(px[2], lo.z); px[3] = blend_px(px[3], lo.w);
+      px[4] = blend_px(px[4], hi.x); px[5] = blend_px(px[5], hi.y); px[6] = blend_px(px[6], hi.z); px[7] = blend_px(px[7], hi.w);
+    }
+  }
+}
+
+__device__ __forceinline__ void fixed_row(uint32_t px[8], const uint8_t* __restrict__ s_atlas, int sprite, int py) {
+  const uint8_t* t = s_atlas + (sprite * 4) * 256 + py * 16;
+  const uint4 lo = *reinterpret_cast<const uint4*>(t);
+  const uint4 hi = *reinterpret_cast<const uint4*>(t + 128);
+  px[0] = lo.x; px[1] = lo.y; px[2] = lo.z; px[3] = lo.w; px[4] = hi.x; px[5] = hi.y; px[6] = hi.z; px[7] = hi.w;
+}
+
+// 8 RGBA pixels -> 24 packed RGB bytes at `dst` (8-byte aligned).
+__device__ __forceinline__ void store_row(uint8_t* dst, const uint32_t px[8]) {
+  uint2 a, b, c;
+  a.x = __byte_perm(px[0], px[1], 0x4210); a.y = __byte_perm(px[1], px[2], 0x5421);
+  b.x = __byte_perm(px[2], px[3], 0x6542); b.y = __byte_perm(px[4], px[5], 0x4210);
+  c.x = __byte_perm(px[5], px[6], 0x5421); c.y = __byte_perm(px[6], px[7], 0x6542);
+  uint2* d = reinterpret_cast<uint2*>(dst);
+  d[0] = a; d[1] = b; d[2] = c;
+}
+
+#define RENDER_THREADS 256
+
+__global__ void __launch_bounds__(RENDER_THREADS, 2) k_render(Tables T, State S, RenderPlan R, uint32_t flags) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // [0] atlas, [1] grid0, [2] grid1
+  uint8_t* s_atlas = smem + R.off_atlas;
+  uint8_t* s_grid_base = smem + R.off_grid0;
+  const int grid_stride = R.off_grid1 - R.off_grid0;
+  uint16_t* s_mask = reinterpret_cast<uint16_t*>(smem + R.off_mask);
+  int16_t* s_map = reinterpret_cast<int16_t*>(smem + R.off_map);  // [P+1][n_sprites]
+  uint8_t* s_tile_base = smem + R.off_tile0;
+  const int tile_stride = R.off_tile1 - R.off_tile0;
+  __shared__ uint8_t s_opaque[256];
+  __shared__ int s_av[MP_MAX_PLAYERS * 4];
+
+  const int tid = threadIdx.x;
+  const int first = blockIdx.x;
+  if (first >= S.B) return;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar[0], (uint32_t)R.atlas_bytes);
+    bulk_load(s_atlas, T.atlas, (uint32_t)R.atlas_bytes, &bar[0]);
+    mbar_expect_tx(&bar[1], (uint32_t)R.grid_bytes);
+    bulk_load(s_grid_base, S.grid + (size_t)first * T.L * T.cells_pad, (uint32_t)R.grid_bytes, &bar[1]);
+  }
+  for (int i = tid; i < (T.P + 1) * T.n_sprites; i += RENDER_THREADS) s_map[i] = T.sprite_map[i];
+  for (int i = tid; i < T.n_sprites; i += RENDER_THREADS) s_opaque[i] = T.sprite_opaque[i];
+#ifndef MP_DEBUG_NOFIX
+  __syncthreads();
+#endif
+  mbar_wait(&bar[0], 0);
+
+  uint32_t tiles_done = 0;
+  int it = 0;
+  for (int b = first; b < S.B; b += gridDim.x, ++it) {
+    const int gb = it & 1;
+    const uint16_t* s_grid = reinterpret_cast<const uint16_t*>(s_grid_base + gb * grid_stride);
+    // prefetch the next env's grid into the other buffer (its last reader finished an iteration ago)
+    const int nb = b + gridDim.x;
+    if (tid == 0 && nb < S.B) {
+      mbar_expect_tx(&bar[1 + (gb ^ 1)], (uint32_t)R.grid_bytes);
+      bulk_load(s_grid_base + (gb ^ 1) * grid_stride, S.grid + (size_t)nb * T.L * T.cells_pad, (uint32_t)R.grid_bytes, &bar[1 + (gb ^ 1)]);
+    }
+    if (tid < T.P * 4) s_av[tid] = S.avatar[(size_t)b * T.P * 4 + tid];
+    mbar_wait(&bar[1 + gb], (uint32_t)((it >> 1) & 1));
+    // Per-cell layer mask: top-down until a fully opaque sprite (everything below is hidden).
+    for (int c = tid; c < T.cells; c += RENDER_THREADS) {
+      uint32_t m = 0;
+      for (int l = T.L - 1; l >= 0; --l) {
+        const int v = s_grid[l * T.cells_pad + c];
+        if (v) { m |= 1u << l; if (s_opaque[(v - 1) >> 2]) break; }
+      }
+      s_mask[c] = (uint16_t)m;
+    }
+    __syncthreads();
+
+    const int n_tiles = ((flags & 2u) ? T.P : 0) + ((flags & 1u) ? R.n_bands : 0);
+    for (int t = 0; t < n_tiles; ++t, ++tiles_done) {
+      const int tb = tiles_done & 1;
+      uint8_t* tile = s_tile_base + tb * tile_stride;
+      if (tid == 0) bulk_wait_read<1>();  // the store issued from this buffer two tiles ago has drained
+      __syncthreads();
+      const bool is_player = (flags & 2u) && t < T.P;
+      uint8_t* gdst; uint32_t gbytes;
+      if (is_player) {
+        const int p = t;
+        const int ax = s_av[p * 4 + AV_X], ay = s_av[p * 4 + AV_Y], ao = s_av[p * 4 + AV_ORIENT], alive = s_av[p * 4 + AV_ALIVE];
+        const int16_t* map = s_map + p * T.n_sprites;
+        const int fdx = dir_dx(ao), fdy = dir_dy(ao), rdx = dir_dx((ao + 1) & 3), rdy = dir_dy((ao + 1) & 3);
+        const int row_bytes = R.view_w * 24;
+        const int n_items = R.view_w * R.view_h * 8;
+        for (int i = tid; i < n_items; i += RENDER_THREADS) {
+          const int c = i >> 3, py = i & 7;
+          const int cy = (int)(((uint32_t)c * R.magic_view_w) >> 16), cx = c - cy * R.view_w;
+          uint32_t px[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          if (!alive) {
+            fixed_row(px, s_atlas, T.oov_sprite, py);  // policy A.13
+          } else {
+            const int dr = cx - T.view_l, df = T.view_f - cy;
+            int wx = ax + rdx * dr + fdx * df, wy = ay + rdy * dr + fdy * df;
+            if (!wrap_or_reject(T, wx, wy)) fixed_row(px, s_atlas, T.oob_sprite, py);
+            else {
+              const int cell = wy * T.W + wx;
+              compose_row(px, s_atlas, s_grid, map, s_opaque, T.cells_pad, cell, s_mask[cell], ao, py);
+            }
+          }
+          store_row(tile + (cy * 8 + py) * row_bytes + cx * 24, px);
+        }
+        gdst = S.rgb + ((size_t)b * T.P + p) * R.player_bytes;
+        gbytes = (uint32_t)R.player_bytes;
+      } else {
+        const int band = t - ((flags & 2u) ? T.P : 0);
+        const int row0 = band * R.band_rows;
+        const int rows = min(R.band_rows, T.H - row0);
+        const int16_t* map = s_map + T.P * T.n_sprites;
+        const int row_bytes = T.W * 24;
+        const int n_items = rows * T.W * 8;
+        for (int i = tid; i < n_items; i += RENDER_THREADS) {
+          const int c = i >> 3, py = i & 7;
+          const int cy = (int)(((uint32_t)c * R.magic_world_w) >> 16), cx = c - cy * T.W;
+          const int cell = (row0 + cy) * T.W + cx;
+          uint32_t px[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#ifdef MP_DEBUG_RENDER
+          if (b == 0 && py == 0 && (int)(flags >> 8) == cell) {
+            printf("dbg cell %d mask %x opaque5 %d L %d:", cell, (unsigned)s_mask[cell], (int)s_opaque[5], T.L);
+            for (int l = 0; l < T.L; ++l) printf(" %d", (int)s_grid[l * T.cells_pad + cell]);
+            printf("\n");
+          }
+#endif
+          compose_row(px, s_atlas, s_grid, map, s_opaque, T.cells_pad, cell, s_mask[cell], 0, py);
+          store_row(tile + (cy * 8 + py) * row_bytes + cx * 24, px);
+        }
+        gdst = S.world_rgb + (size_t)b * R.world_bytes + (size_t)row0 * 8 * row_bytes;
+        gbytes = (uint32_t)(rows * 8 * row_bytes);
+      }
+      fence_async_smem();  // make this thread's tile writes visible to the async (TMA) proxy
+      __syncthreads();
+      if (tid == 0) bulk_store(gdst, tile, gbytes);
+    }
+    __syncthreads();  // all readers of s_grid / s_mask / s_av are done before the next env overwrites them
+  }
+  if (tid == 0) bulk_wait_read<0>();
+}

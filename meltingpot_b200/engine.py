@@ -1,0 +1,249 @@
+"""ctypes binding of libmpengine.so (include/mp_engine.h) + zero-copy torch views.
+
+PyTorch is used only to wrap the engine's device buffers as tensors and to supply
+streams; all compute is in the library's CUDA kernels. There is no CPU path: if
+the library or a CUDA device is missing, construction raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get('MP_ENGINE_LIB') or os.path.join(_HERE, 'libmpengine.so')
+
+MP_FLAG_RENDER_WORLD = 1
+MP_FLAG_RENDER_PLAYERS = 2
+MP_FLAG_DEFAULT = 3
+
+EXPORTED_SYMBOLS = (
+    'mp_create', 'mp_destroy', 'mp_set_flags', 'mp_reset', 'mp_step',
+    'mp_step_state', 'mp_render', 'mp_get_buffers', 'mp_step_host',
+    'mp_reset_host', 'mp_launch_count', 'mp_algorithmic_bytes',
+    'mp_last_error', 'mp_version',
+)
+
+
+class MpBuffers(ctypes.Structure):
+  _fields_ = [
+      ('num_envs', ctypes.c_int32), ('num_players', ctypes.c_int32),
+      ('rgb_h', ctypes.c_int32), ('rgb_w', ctypes.c_int32),
+      ('world_h', ctypes.c_int32), ('world_w', ctypes.c_int32),
+      ('num_actions', ctypes.c_int32), ('num_scalar_obs', ctypes.c_int32),
+      ('rgb', ctypes.c_void_p), ('world_rgb', ctypes.c_void_p),
+      ('reward', ctypes.c_void_p), ('discount', ctypes.c_void_p),
+      ('step_type', ctypes.c_void_p), ('scalar_obs', ctypes.c_void_p),
+      ('avatar_state', ctypes.c_void_p), ('grid', ctypes.c_void_p),
+      ('grid_layers', ctypes.c_int32), ('grid_cells', ctypes.c_int32),
+      ('grid_cells_padded', ctypes.c_int32),
+  ]
+
+
+class MpHostOutputs(ctypes.Structure):
+  _fields_ = [
+      ('rgb', ctypes.c_void_p), ('world_rgb', ctypes.c_void_p),
+      ('reward', ctypes.c_void_p), ('discount', ctypes.c_void_p),
+      ('step_type', ctypes.c_void_p), ('scalar_obs', ctypes.c_void_p),
+  ]
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+  """Loads libmpengine.so; raises if it has not been built (no fallback)."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise RuntimeError(
+        f'{LIB_PATH} is missing: build it with `python -m meltingpot_b200.build` '
+        '(the engine has no CPU or PyTorch fallback)')
+  lib = ctypes.CDLL(LIB_PATH)
+  vp = ctypes.c_void_p
+  lib.mp_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int,
+                            ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64,
+                            ctypes.c_uint32, ctypes.POINTER(vp)]
+  lib.mp_destroy.argtypes = [vp]
+  lib.mp_set_flags.argtypes = [vp, ctypes.c_uint32]
+  lib.mp_reset.argtypes = [vp, vp, vp]
+  lib.mp_step.argtypes = [vp, vp, vp]
+  lib.mp_step_state.argtypes = [vp, vp, vp]
+  lib.mp_render.argtypes = [vp, vp]
+  lib.mp_get_buffers.argtypes = [vp, ctypes.POINTER(MpBuffers)]
+  lib.mp_step_host.argtypes = [vp, vp, ctypes.POINTER(MpHostOutputs), vp]
+  lib.mp_reset_host.argtypes = [vp, ctypes.POINTER(MpHostOutputs), vp]
+  lib.mp_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
+  lib.mp_algorithmic_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64),
+                                       ctypes.POINTER(ctypes.c_uint64)]
+  lib.mp_last_error.restype = ctypes.c_char_p
+  lib.mp_version.restype = ctypes.c_char_p
+  _lib = lib
+  return lib
+
+
+class EngineError(RuntimeError):
+  pass
+
+
+def _check(rc: int) -> None:
+  if rc != 0:
+    msg = load_library().mp_last_error().decode('utf-8', 'replace')
+    if rc in (-1, -2):
+      raise ValueError(f'mp_engine error {rc}: {msg}')
+    raise EngineError(f'mp_engine error {rc}: {msg}')
+
+
+class _CudaView:
+  """Exposes a raw device pointer through __cuda_array_interface__ (v2)."""
+
+  def __init__(self, ptr: int, shape, typestr: str, owner):
+    self._owner = owner  # keeps the engine alive while tensors exist
+    self.__cuda_array_interface__ = {
+        'shape': tuple(int(s) for s in shape), 'typestr': typestr,
+        'data': (int(ptr), False), 'version': 2, 'strides': None,
+    }
+
+
+class Engine:
+  """One engine handle = `num_envs` env instances on one GPU."""
+
+  def __init__(self, blob: bytes, num_envs: int, device: int = 0, seed: int = 1,
+               env_index_base: int = 0, flags: int = MP_FLAG_DEFAULT):
+    import torch  # pylint: disable=g-import-not-at-top
+    if not torch.cuda.is_available():
+      raise EngineError('CUDA is not available: the B200 engine has no CPU path')
+    self._torch = torch
+    self._lib = load_library()
+    self._blob = bytes(blob)
+    self.device = int(device)
+    self.num_envs = int(num_envs)
+    torch.cuda.init()
+    with torch.cuda.device(self.device):
+      torch.cuda.current_stream()  # make sure the primary context exists
+    handle = ctypes.c_void_p()
+    _check(self._lib.mp_create(self._blob, len(self._blob), self.num_envs,
+                               self.device, ctypes.c_uint64(seed),
+                               ctypes.c_uint64(env_index_base),
+                               ctypes.c_uint32(flags), ctypes.byref(handle)))
+    self._h = handle
+    bufs = MpBuffers()
+    _check(self._lib.mp_get_buffers(self._h, ctypes.byref(bufs)))
+    self.buffers = bufs
+    self.num_players = int(bufs.num_players)
+    self.num_actions = int(bufs.num_actions)
+    self.num_scalar_obs = int(bufs.num_scalar_obs)
+    B, P = self.num_envs, self.num_players
+    dev = torch.device('cuda', self.device)
+
+    def view(ptr, shape, typestr, dtype):
+      return torch.as_tensor(_CudaView(ptr, shape, typestr, self), device=dev, dtype=dtype)
+
+    self.rgb = view(bufs.rgb, (B, P, bufs.rgb_h, bufs.rgb_w, 3), '|u1', torch.uint8)
+    self.world_rgb = view(bufs.world_rgb, (B, bufs.world_h, bufs.world_w, 3), '|u1', torch.uint8)
+    self.reward = view(bufs.reward, (B, P), '<f8', torch.float64)
+    self.discount = view(bufs.discount, (B,), '<f8', torch.float64)
+    self.step_type = view(bufs.step_type, (B,), '<i8', torch.int64)
+    self.scalar_obs = view(bufs.scalar_obs, (max(self.num_scalar_obs, 1), B, P), '<f8', torch.float64)
+    self.avatar_state = view(bufs.avatar_state, (B, P, 4), '<i4', torch.int32)
+    self.grid = view(bufs.grid, (B, bufs.grid_layers, bufs.grid_cells_padded), '<i2', torch.int16)
+
+  # -- lifecycle -----------------------------------------------------------------
+  def close(self) -> None:
+    if getattr(self, '_h', None):
+      self._lib.mp_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+  def _stream(self, stream) -> ctypes.c_void_p:
+    if stream is None:
+      stream = self._torch.cuda.current_stream(self.device)
+    return ctypes.c_void_p(stream.cuda_stream)
+
+  # -- device-resident API ---------------------------------------------------------
+  def set_flags(self, flags: int) -> None:
+    _check(self._lib.mp_set_flags(self._h, ctypes.c_uint32(flags)))
+
+  def reset(self, mask=None, stream=None) -> None:
+    ptr = None
+    if mask is not None:
+      assert mask.dtype == self._torch.uint8 and mask.is_cuda and mask.numel() == self.num_envs
+      ptr = ctypes.c_void_p(mask.data_ptr())
+    _check(self._lib.mp_reset(self._h, ptr, self._stream(stream)))
+
+  def step(self, actions, stream=None) -> None:
+    """actions: int32 CUDA tensor [B, P] of discrete action ids."""
+    self._check_actions(actions)
+    _check(self._lib.mp_step(self._h, ctypes.c_void_p(actions.data_ptr()), self._stream(stream)))
+
+  def step_state(self, actions, stream=None) -> None:
+    self._check_actions(actions)
+    _check(self._lib.mp_step_state(self._h, ctypes.c_void_p(actions.data_ptr()), self._stream(stream)))
+
+  def render(self, stream=None) -> None:
+    _check(self._lib.mp_render(self._h, self._stream(stream)))
+
+  def _check_actions(self, actions) -> None:
+    torch = self._torch
+    if (actions.dtype != torch.int32 or not actions.is_cuda or not actions.is_contiguous()
+        or actions.shape != (self.num_envs, self.num_players)
+        or actions.device.index != self.device):
+      raise ValueError('actions must be a contiguous int32 CUDA tensor [B, P] on the engine device')
+
+  # -- host-buffer API (end-to-end path) -----------------------------------------
+  def make_host_outputs(self, rgb=True, world_rgb=True) -> Dict[str, 'np.ndarray']:
+    """Pinned host tensors for mp_step_host, as a dict of torch CPU tensors."""
+    torch = self._torch
+    b = self.buffers
+    B, P = self.num_envs, self.num_players
+    out = {
+        'reward': torch.empty((B, P), dtype=torch.float64).pin_memory(),
+        'discount': torch.empty((B,), dtype=torch.float64).pin_memory(),
+        'step_type': torch.empty((B,), dtype=torch.int64).pin_memory(),
+        'scalar_obs': torch.empty((max(self.num_scalar_obs, 1), B, P), dtype=torch.float64).pin_memory(),
+    }
+    if rgb:
+      out['rgb'] = torch.empty((B, P, b.rgb_h, b.rgb_w, 3), dtype=torch.uint8).pin_memory()
+    if world_rgb:
+      out['world_rgb'] = torch.empty((B, b.world_h, b.world_w, 3), dtype=torch.uint8).pin_memory()
+    return out
+
+  @staticmethod
+  def _host_struct(outputs) -> MpHostOutputs:
+    s = MpHostOutputs()
+    for name in ('rgb', 'world_rgb', 'reward', 'discount', 'step_type', 'scalar_obs'):
+      t = outputs.get(name) if outputs else None
+      setattr(s, name, ctypes.c_void_p(t.data_ptr()) if t is not None else None)
+    return s
+
+  def step_host(self, actions_host, outputs, stream=None) -> None:
+    """actions_host: int32 CPU tensor [B, P] (pinned for full speed)."""
+    assert actions_host.dtype == self._torch.int32 and not actions_host.is_cuda
+    assert actions_host.is_contiguous() and actions_host.shape == (self.num_envs, self.num_players)
+    s = self._host_struct(outputs)
+    _check(self._lib.mp_step_host(self._h, ctypes.c_void_p(actions_host.data_ptr()),
+                                  ctypes.byref(s), self._stream(stream)))
+
+  def reset_host(self, outputs, stream=None) -> None:
+    s = self._host_struct(outputs)
+    _check(self._lib.mp_reset_host(self._h, ctypes.byref(s), self._stream(stream)))
+
+  # -- introspection -----------------------------------------------------------------
+  def launch_count(self) -> int:
+    n = ctypes.c_uint64(0)
+    _check(self._lib.mp_launch_count(self._h, ctypes.byref(n)))
+    return int(n.value)
+
+  def algorithmic_bytes(self):
+    a, r = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    _check(self._lib.mp_algorithmic_bytes(self._h, ctypes.byref(a), ctypes.byref(r)))
+    return int(a.value), int(r.value)

@@ -60,6 +60,13 @@ def lib() -> ctypes.CDLL:
     L.oracle_run_random.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_uint64, ctypes.c_int,
                                     ctypes.POINTER(ctypes.c_uint64)]
+    L.oracle_batch_create.restype = vp
+    L.oracle_batch_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64]
+    L.oracle_batch_destroy.argtypes = [vp]
+    L.oracle_batch_step_random.restype = ctypes.c_long
+    L.oracle_batch_step_random.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.oracle_batch_checksum.restype = ctypes.c_uint64
+    L.oracle_batch_checksum.argtypes = [vp]
     _lib = L
   return _lib
 
@@ -185,3 +192,31 @@ def run_random(blob: bytes, n_envs: int, n_steps: int, n_threads: int,
   n = lib().oracle_run_random(bytes(blob), len(blob), n_envs, n_steps, n_threads,
                               ctypes.c_uint64(seed), int(render), ctypes.byref(chk))
   return int(n), int(chk.value)
+
+
+class OracleBatch:
+  """Persistent set of CPU envs stepped with uniform-random actions on host threads."""
+
+  def __init__(self, blob: bytes, n_envs: int, seed: int = 1):
+    self._blob = bytes(blob)
+    self.n_envs = n_envs
+    self._h = lib().oracle_batch_create(self._blob, len(self._blob), n_envs, ctypes.c_uint64(seed))
+    if not self._h:
+      raise RuntimeError('oracle_batch_create failed')
+
+  def step_random(self, n_steps: int, n_threads: int, render: bool = True) -> int:
+    return int(lib().oracle_batch_step_random(self._h, n_steps, n_threads, int(render)))
+
+  def checksum(self) -> int:
+    return int(lib().oracle_batch_checksum(self._h))
+
+  def close(self):
+    if self._h:
+      lib().oracle_batch_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass

@@ -817,3 +817,61 @@ long oracle_run_random(const void* blob, size_t n, int n_envs, int n_steps, int 
   if (checksum) *checksum = sum;
   return total;
 }
+
+/* Persistent batch for the CPU baseline / reference arm: envs live across calls. */
+typedef struct OrBatch { int n_envs; OrEnv** envs; uint64_t* rng; uint8_t** rgb; uint8_t** world; uint64_t sum; } OrBatch;
+OrBatch* oracle_batch_create(const void* blob, size_t n, int n_envs, uint64_t seed) {
+  OrBatch* bt = (OrBatch*)calloc(1, sizeof(OrBatch));
+  bt->n_envs = n_envs;
+  bt->envs = (OrEnv**)calloc(n_envs, sizeof(OrEnv*)); bt->rng = (uint64_t*)calloc(n_envs, sizeof(uint64_t));
+  bt->rgb = (uint8_t**)calloc(n_envs, sizeof(uint8_t*)); bt->world = (uint8_t**)calloc(n_envs, sizeof(uint8_t*));
+  for (int b = 0; b < n_envs; ++b) {
+    OrEnv* e = oracle_create(blob, n, seed + (uint64_t)b);
+    if (!e) return 0;
+    bt->envs[b] = e; bt->rng[b] = seed * 0x2545F4914F6CDD1Dull + (uint64_t)b;
+    int vw = e->view_l + e->view_r + 1, vh = e->view_f + e->view_b + 1;
+    bt->rgb[b] = (uint8_t*)malloc((size_t)vw * vh * e->S * e->S * 3);
+    bt->world[b] = (uint8_t*)malloc((size_t)e->W * e->H * e->S * e->S * 3);
+    oracle_reset(e);
+  }
+  return bt;
+}
+void oracle_batch_destroy(OrBatch* bt) {
+  if (!bt) return;
+  for (int b = 0; b < bt->n_envs; ++b) { oracle_destroy(bt->envs[b]); free(bt->rgb[b]); free(bt->world[b]); }
+  free(bt->envs); free(bt->rng); free(bt->rgb); free(bt->world); free(bt);
+}
+typedef struct { OrBatch* bt; int b0, b1, n_steps, render; long total; uint64_t sum; } BatchArgs;
+static void* batch_worker(void* argp) {
+  BatchArgs* a = (BatchArgs*)argp;
+  int32_t act[OR_MAX_PLAYERS]; double rew[OR_MAX_PLAYERS];
+  for (int b = a->b0; b < a->b1; ++b) {
+    OrEnv* e = a->bt->envs[b];
+    for (int t = 0; t < a->n_steps; ++t) {
+      for (int p = 0; p < e->P; ++p) act[p] = (int32_t)(splitmix64(&a->bt->rng[b]) % (uint64_t)e->n_actions);
+      oracle_step(e, act);
+      oracle_get_rewards(e, rew);
+      for (int p = 0; p < e->P; ++p) a->sum += (uint64_t)rew[p];
+      if (a->render) { for (int p = 0; p < e->P; ++p) { oracle_render_player(e, p, a->bt->rgb[b]); a->sum += a->bt->rgb[b][1000]; } oracle_render_world(e, a->bt->world[b]); a->sum += a->bt->world[b][5000]; }
+      ++a->total;
+    }
+  }
+  return 0;
+}
+/* Steps every env `n_steps` times with uniform-random actions on `n_threads` threads. */
+long oracle_batch_step_random(OrBatch* bt, int n_steps, int n_threads, int render) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > bt->n_envs) n_threads = bt->n_envs;
+  pthread_t* th = (pthread_t*)calloc(n_threads, sizeof(pthread_t));
+  BatchArgs* args = (BatchArgs*)calloc(n_threads, sizeof(BatchArgs));
+  for (int t = 0; t < n_threads; ++t) {
+    BatchArgs a = {bt, (int)((long)bt->n_envs * t / n_threads), (int)((long)bt->n_envs * (t + 1) / n_threads), n_steps, render, 0, 0};
+    args[t] = a;
+    pthread_create(&th[t], 0, batch_worker, &args[t]);
+  }
+  long total = 0;
+  for (int t = 0; t < n_threads; ++t) { pthread_join(th[t], 0); total += args[t].total; bt->sum += args[t].sum; }
+  free(th); free(args);
+  return total;
+}
+uint64_t oracle_batch_checksum(const OrBatch* bt) { return bt->sum; }

@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+  config.addinivalue_line('markers', 'gpu: needs a real B200 (run with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def clean_up_blob():
+  from meltingpot_b200 import substrates
+  return substrates.load_blob('clean_up')
+
+
+@pytest.fixture(scope='session')
+def oracle():
+  from oracle import binding
+  binding.build()
+  return binding
