@@ -68,9 +68,10 @@ struct Tables {
   const int16_t* apple_of_cell;  // [cells_pad] apple index or -1
   const int16_t* dirt_of_cell;   // [cells_pad] dirt index or -1
   // render tables
-  const uint8_t* atlas;        // [n_sprites][4][2][8][16]: facing, half (px 0-3 | 4-7), row, 16 B
-  const int16_t* sprite_map;   // [P+1][n_sprites]
-  const uint8_t* sprite_opaque;  // [n_sprites] 1 = every pixel alpha 255 and never remapped
+  const uint8_t* atlas;        // [n_total][4][2][8][16]: facing, half (px 0-3 | 4-7), row, 16 B (n_total includes pre-merged sprites)
+  const int16_t* sprite_map;   // [P+1][n_total]
+  const uint8_t* sprite_opaque;  // [n_total] 1 = every pixel alpha 255 and never remapped
+  const uint8_t* sprite_pair;    // [n_total][n_total] pre-merged sprite for (opaque base, sprite on top) or 0
 };
 
 struct State {

@@ -85,6 +85,7 @@ struct mp_engine {
   int B = 0;
   uint32_t flags = MP_FLAG_DEFAULT;
   int family = 0;
+  int n_total = 0;  // atlas sprites incl. pre-merged
   Tables T{};
   State S{};
   RenderPlan R{};
@@ -220,25 +221,127 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   for (int j = 0; j < T.nD; ++j) { dirt_of[v_dirt[j * 3 + 1]] = (int16_t)j; T.dirt_count0 += v_dirt[j * 3 + 2]; }
   if ((rc = E->upload(apple_of, &T.apple_of_cell)) || (rc = E->upload(dirt_of, &T.dirt_of_cell))) return rc;
 
-  // render tables: atlas re-laid out as [sprite][facing][half][row][16 B] so that the 8 rows of one
-  // half are 128 contiguous bytes (conflict-free 128-bit shared loads).
+  // ---- render tables ------------------------------------------------------------------------------
   if (atlas.count != (size_t)T.n_sprites * 1024) return fail(MP_E_INVALID, "atlas has %zu bytes, expected %d", atlas.count, T.n_sprites * 1024);
-  std::vector<uint8_t> at(atlas.count);
-  for (int s = 0; s < T.n_sprites * 4; ++s)
+  std::vector<uint8_t> img(atlas.data, atlas.data + atlas.count);  // [sprite][facing][row][px][4]
+  std::vector<uint8_t> opq(sprite_opaque.data, sprite_opaque.data + T.n_sprites);
+  std::vector<uint8_t> remapped(T.n_sprites, 0);
+  for (int v = 0; v <= T.P; ++v)
+    for (int s = 0; s < T.n_sprites; ++s)
+      if (sprite_map.data[(size_t)v * T.n_sprites + s] != s) { remapped[s] = 1; opq[s] = 0; }  // a remapped sprite must not hide layers
+  // Pre-merged sprites. For every stack of map pieces that can occur on a cell, the opaque bottom
+  // sprite and the sprites above it are folded pairwise into new opaque sprites using exactly the
+  // renderer's arithmetic (policy A.14), so the kernel composes most cells with a single copy.
+  std::vector<std::vector<int>> pair_of;  // pair_of[base][top] -> merged id (grown with the atlas)
+  auto n_now = [&]() { return (int)opq.size(); };
+  pair_of.assign(T.n_sprites, std::vector<int>());
+  auto blend = [](uint8_t* d, const uint8_t* s_) {
+    unsigned a = s_[3];
+    if (a == 255) { d[0] = s_[0]; d[1] = s_[1]; d[2] = s_[2]; }
+    else if (a) for (int c = 0; c < 3; ++c) d[c] = (uint8_t)((s_[c] * a + d[c] * (255u - a)) / 255u);
+  };
+  auto merged_id = [&](int base, int top) -> int {
+    if ((int)pair_of[base].size() <= top) pair_of[base].resize(top + 1, 0);
+    if (pair_of[base][top]) return pair_of[base][top];
+    if (n_now() >= 255) return 0;
+    int id = n_now();
+    img.resize((size_t)(id + 1) * 1024);
+    for (int f = 0; f < 4; ++f)
+      for (int px = 0; px < 64; ++px) {
+        uint8_t* d = &img[(size_t)id * 1024 + f * 256 + px * 4];
+        memcpy(d, &img[(size_t)base * 1024 + f * 256 + px * 4], 4);
+        blend(d, &img[(size_t)top * 1024 + f * 256 + px * 4]);
+        d[3] = 255;
+      }
+    opq.push_back(1); remapped.push_back(0);
+    pair_of.push_back(std::vector<int>());
+    pair_of[base][top] = id;
+    return id;
+  };
+  {
+    struct Opt { std::vector<int> sprites; bool absent = false; int orient = -1; bool bad = false; };
+    std::vector<Opt> opts((size_t)T.cells * T.L);
+    std::vector<uint8_t> has_obj((size_t)T.cells * T.L, 0);
+    for (int o = 0; o < m[MPB_META_N_OBJECTS]; ++o) {
+      const int32_t* od = objects.data + o * MPB_OBJ_COLS;
+      const int32_t* kd = kinds.data + od[MPB_OBJ_KIND] * MPB_KIND_COLS;
+      if (kd[MPB_KIND_IS_AVATAR]) continue;
+      const int cell = od[MPB_OBJ_Y] * T.W + od[MPB_OBJ_X];
+      const int ns = kd[MPB_KIND_NSTATES];
+      for (int si = 0; si < ns; ++si) {
+        const int32_t* st = states.data + (kd[MPB_KIND_STATE0] + si) * MPB_STATE_COLS;
+        const int l = st[MPB_STATE_LAYER], sp = st[MPB_STATE_SPRITE];
+        if (l < 0 || sp < 0) continue;
+        Opt& op = opts[(size_t)cell * T.L + l];
+        if (std::find(op.sprites.begin(), op.sprites.end(), sp) == op.sprites.end()) op.sprites.push_back(sp);
+        if (op.orient >= 0 && op.orient != od[MPB_OBJ_ORIENT]) op.bad = true;
+        op.orient = od[MPB_OBJ_ORIENT];
+        // the piece may also be somewhere else (another layer / off grid / sprite-less state)
+        for (int sj = 0; sj < ns; ++sj) {
+          const int32_t* s2 = states.data + (kd[MPB_KIND_STATE0] + sj) * MPB_STATE_COLS;
+          if (s2[MPB_STATE_LAYER] != l || s2[MPB_STATE_SPRITE] < 0) op.absent = true;
+        }
+      }
+    }
+    std::vector<int> stack_s, stack_o;
+    for (int cell = 0; cell < T.cells; ++cell) {
+      // enumerate the cartesian product of per-layer options, bottom up (bounded)
+      size_t combos = 1;
+      bool bad = false;
+      for (int l = 0; l < T.L; ++l) {
+        const Opt& op = opts[(size_t)cell * T.L + l];
+        bad |= op.bad;
+        combos *= std::max<size_t>(1, op.sprites.size() + ((op.absent || op.sprites.empty()) ? 1 : 0));
+        if (combos > 4096) { bad = true; break; }
+      }
+      if (bad) continue;
+      std::vector<int> idx(T.L, 0);
+      for (size_t k = 0; k < combos; ++k) {
+        stack_s.clear(); stack_o.clear();
+        for (int l = 0; l < T.L; ++l) {
+          const Opt& op = opts[(size_t)cell * T.L + l];
+          const int i = idx[l];
+          if (i < (int)op.sprites.size()) { stack_s.push_back(op.sprites[i]); stack_o.push_back(op.orient); }
+        }
+        // the walk the kernel performs: opaque bottom, then fold upwards while possible
+        int j = -1;
+        for (int q = (int)stack_s.size() - 1; q >= 0; --q) if (opq[stack_s[q]]) { j = q; break; }
+        if (j >= 0) {
+          int cur = stack_s[j];
+          for (int q = j + 1; q < (int)stack_s.size(); ++q) {
+            const int t = stack_s[q];
+            if (stack_o[q] != stack_o[j] || remapped[t] || remapped[cur]) break;
+            cur = merged_id(cur, t);
+            if (!cur) break;
+          }
+        }
+        for (int l = 0; l < T.L; ++l) {  // next combination
+          const Opt& op = opts[(size_t)cell * T.L + l];
+          const int radix = (int)std::max<size_t>(1, op.sprites.size() + ((op.absent || op.sprites.empty()) ? 1 : 0));
+          if (++idx[l] < radix) break;
+          idx[l] = 0;
+        }
+      }
+    }
+  }
+  const int n_total = n_now();
+  E->n_total = n_total;
+  // atlas re-laid out as [sprite][facing][half][row][16 B] so that the 8 rows of one half are 128
+  // contiguous bytes (conflict-free 128-bit shared loads).
+  std::vector<uint8_t> at((size_t)n_total * 1024);
+  for (int s = 0; s < n_total * 4; ++s)
     for (int row = 0; row < 8; ++row)
       for (int half = 0; half < 2; ++half)
-        memcpy(&at[(size_t)s * 256 + half * 128 + row * 16], atlas.data + (size_t)s * 256 + row * 32 + half * 16, 16);
+        memcpy(&at[(size_t)s * 256 + half * 128 + row * 16], &img[(size_t)s * 256 + row * 32 + half * 16], 16);
   if ((rc = E->upload(at, &T.atlas))) return rc;
-  std::vector<int16_t> smap((size_t)(T.P + 1) * T.n_sprites);
-  std::vector<uint8_t> opq(T.n_sprites);
-  for (int s = 0; s < T.n_sprites; ++s) opq[s] = sprite_opaque.data[s];
+  std::vector<int16_t> smap((size_t)(T.P + 1) * n_total);
   for (int v = 0; v <= T.P; ++v)
-    for (int s = 0; s < T.n_sprites; ++s) {
-      int to = sprite_map.data[(size_t)v * T.n_sprites + s];
-      smap[(size_t)v * T.n_sprites + s] = (int16_t)to;
-      if (to != s) opq[s] = 0;  // a remapped sprite must not cut the layer walk short
-    }
-  if ((rc = E->upload(smap, &T.sprite_map)) || (rc = E->upload(opq, &T.sprite_opaque))) return rc;
+    for (int s = 0; s < n_total; ++s)
+      smap[(size_t)v * n_total + s] = (int16_t)(s < T.n_sprites ? sprite_map.data[(size_t)v * T.n_sprites + s] : s);
+  std::vector<uint8_t> pair((size_t)n_total * n_total, 0);
+  for (int b = 0; b < n_total; ++b)
+    for (int t = 0; t < (int)pair_of[b].size(); ++t) pair[(size_t)b * n_total + t] = (uint8_t)pair_of[b][t];
+  if ((rc = E->upload(smap, &T.sprite_map)) || (rc = E->upload(opq, &T.sprite_opaque)) || (rc = E->upload(pair, &T.sprite_pair))) return rc;
   return MP_OK;
 }
 
@@ -253,18 +356,23 @@ int build_plan(mp_engine* E) {
   R.world_bytes = T.H * cell_row_bytes;
   R.tile_bytes = round_up(std::max(R.player_bytes, R.band_rows * cell_row_bytes), 128);
   R.grid_bytes = T.L * T.cells_pad * 2;
-  R.atlas_bytes = T.n_sprites * 1024;
+  R.n_total = E->n_total;
+  R.atlas_bytes = R.n_total * 1024;
+  R.rec_stride = T.L + 1;
   R.magic_view_w = (65536u + R.view_w - 1) / R.view_w;
   R.magic_world_w = (65536u + T.W - 1) / T.W;
   int off = 128;  // mbarriers
   R.off_atlas = off; off += round_up(R.atlas_bytes, 128);
-  R.off_grid0 = off; off += round_up(R.grid_bytes, 128);
-  R.off_grid1 = off; off += round_up(R.grid_bytes, 128);
-  R.off_mask = off; off += round_up(T.cells_pad * 2, 128);
-  R.off_map = off; off += round_up((T.P + 1) * T.n_sprites * 2, 128);
-  R.off_tile0 = off; off += R.tile_bytes;
-  R.off_tile1 = off; off += R.tile_bytes;
-  R.smem_bytes = off;
+  R.off_pair = off; off += round_up(R.n_total * R.n_total, 128);
+  R.off_map = off; off += round_up((T.P + 1) * R.n_total * 2, 128);
+  R.off_team0 = off;
+  int toff = 0;
+  R.toff_grid = toff; toff += round_up(R.grid_bytes, 128);
+  R.toff_rec = toff; toff += round_up(T.cells * R.rec_stride * 2, 128);
+  R.toff_tile0 = toff; toff += R.tile_bytes;
+  R.toff_tile1 = toff; toff += R.tile_bytes;
+  R.team_stride = toff;
+  R.smem_bytes = R.off_team0 + RENDER_TEAMS * R.team_stride;
   if (R.smem_bytes > 227 * 1024) return fail(MP_E_UNSUPPORTED, "render kernel needs %d B of shared memory (> 227 KB)", R.smem_bytes);
   return MP_OK;
 }
@@ -279,7 +387,7 @@ int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int 
 
 int launch_render(mp_engine* E, cudaStream_t st) {
   if (!(E->flags & (MP_FLAG_RENDER_WORLD | MP_FLAG_RENDER_PLAYERS))) return MP_OK;
-  const int blocks = std::min(E->B, E->sm_count * 2);
+  const int blocks = std::min((E->B + RENDER_TEAMS - 1) / RENDER_TEAMS, E->sm_count);
   k_render<<<blocks, RENDER_THREADS, E->R.smem_bytes, st>>>(E->T, E->S, E->R, E->flags);
   ++E->launches;
   CUDA_TRY(cudaGetLastError());

@@ -6,15 +6,26 @@
 // (policies A.11-A.14 of the ledger: view window, sprite facing, out-of-bounds / out-of-view
 // sprites, bottom-to-top alpha compositing in render order).
 //
-// HBM-bound: per env-step it reads the 11 KB sprite grid and writes P*88*88*3 + H*W*192 bytes.
-// One persistent CTA renders whole envs: the sprite atlas is TMA-bulk-copied to shared memory once
-// per CTA, each env's grid is bulk-prefetched (double buffered) behind an mbarrier, images are
-// composed tile by tile in shared memory and leave through cp.async.bulk shared->global stores, so
-// every byte of the observations is written exactly once, fully coalesced, by the copy engine.
+// HBM-bound by design: per env-step it reads the ~11 KB sprite grid and writes
+// P*88*88*3 + H*W*192 bytes of observations. One persistent CTA per SM hosts RENDER_TEAMS
+// independent teams of 256 threads that share one shared-memory copy of the sprite atlas
+// (TMA-bulk-loaded once). Each team renders whole envs:
+//   1. the env's grid arrives by TMA bulk copy behind an mbarrier (prefetched one env ahead);
+//   2. a per-cell pass flattens every cell's layer stack into a short record, folding the opaque
+//      bottom sprite and the map sprites stacked on it into one pre-merged opaque sprite
+//      (merged on the host with exactly the compositing arithmetic, so results stay bit-exact);
+//   3. images are composed tile by tile in shared memory (8 pixels = 24 bytes per thread-item) and
+//      leave through cp.async.bulk shared->global stores, double buffered, so every observation
+//      byte is written once, fully coalesced, by the copy engine.
 #pragma once
 
-#include "common.cuh"
 #include <cstdio>
+
+#include "common.cuh"
+
+#define RENDER_TEAMS 2
+#define TEAM_THREADS 256
+#define RENDER_THREADS (RENDER_TEAMS * TEAM_THREADS)
 
 struct RenderPlan {  // host-computed constants of the tiling
   int view_w, view_h;        // cells
@@ -23,10 +34,14 @@ struct RenderPlan {  // host-computed constants of the tiling
   int world_bytes;
   int tile_bytes;            // shared-memory tile buffer (>= player_bytes, >= band bytes)
   int grid_bytes;            // L * cells_pad * 2
-  int atlas_bytes;
+  int atlas_bytes;           // n_total sprites * 1024
+  int n_total;               // atlas sprites including pre-merged ones
+  int rec_stride;            // u16 per cell record: count + up to L entries
   uint32_t magic_view_w, magic_world_w;  // q = (c * magic) >> 16 == c / w for c < 4096
   // shared memory offsets
-  int off_atlas, off_grid0, off_grid1, off_mask, off_map, off_tile0, off_tile1, smem_bytes;
+  int off_atlas, off_pair, off_map, off_team0, team_stride;
+  int toff_grid, toff_rec, toff_tile0, toff_tile1;  // within a team's region
+  int smem_bytes;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -64,6 +79,7 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(TEAM_THREADS) : "memory"); }
 
 // dst, src: R | G<<8 | B<<16 (| A<<24 for src). Integer "over": (s*a + d*(255-a)) / 255, truncated.
 __device__ __forceinline__ uint32_t blend_px(uint32_t dst, uint32_t src) {
@@ -78,15 +94,13 @@ __device__ __forceinline__ uint32_t blend_px(uint32_t dst, uint32_t src) {
   return rb | (g << 8);
 }
 
-// Composites pixel row `py` of the cell stack at `cell` (bits of `mask` = layers to draw, bottom
-// up) into px[8].
-__device__ __forceinline__ void compose_row(uint32_t px[8], const uint8_t* __restrict__ s_atlas, const uint16_t* __restrict__ s_grid,
-                                            const int16_t* __restrict__ s_map, const uint8_t* __restrict__ opaque, int cells_pad,
-                                            int cell, uint32_t mask, int viewer_orient, int py) {
-  while (mask) {
-    const int l = __ffs(mask) - 1;
-    mask &= mask - 1;
-    const int v = (int)s_grid[l * cells_pad + cell] - 1;
+// Composites pixel row `py` of a flattened cell record into px[8], bottom up.
+__device__ __forceinline__ void compose_record(uint32_t px[8], const uint8_t* __restrict__ s_atlas, const uint16_t* __restrict__ rec,
+                                               const int16_t* __restrict__ s_map, const uint8_t* __restrict__ opaque,
+                                               int viewer_orient, int py) {
+  const int n = rec[0];
+  for (int k = 1; k <= n; ++k) {
+    const int v = (int)rec[k] - 1;
     const int sprite = s_map[v >> 2];
     const int facing = ((v & 3) - viewer_orient) & 3;
     const uint8_t* t = s_atlas + (sprite * 4 + facing) * 256 + py * 16;
@@ -118,83 +132,101 @@ __device__ __forceinline__ void store_row(uint8_t* dst, const uint32_t px[8]) {
   d[0] = a; d[1] = b; d[2] = c;
 }
 
-#define RENDER_THREADS 256
-
-__global__ void __launch_bounds__(RENDER_THREADS, 2) k_render(Tables T, State S, RenderPlan R, uint32_t flags) {
+__global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S, RenderPlan R, uint32_t flags) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // [0] atlas, [1] grid0, [2] grid1
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // [0] atlas, [1 + team] grid
   uint8_t* s_atlas = smem + R.off_atlas;
-  uint8_t* s_grid_base = smem + R.off_grid0;
-  const int grid_stride = R.off_grid1 - R.off_grid0;
-  uint16_t* s_mask = reinterpret_cast<uint16_t*>(smem + R.off_mask);
-  int16_t* s_map = reinterpret_cast<int16_t*>(smem + R.off_map);  // [P+1][n_sprites]
-  uint8_t* s_tile_base = smem + R.off_tile0;
-  const int tile_stride = R.off_tile1 - R.off_tile0;
+  const uint8_t* s_pair = smem + R.off_pair;                          // [n_total][n_total] merged sprite or 0
+  int16_t* s_map = reinterpret_cast<int16_t*>(smem + R.off_map);      // [P+1][n_total]
   __shared__ uint8_t s_opaque[256];
-  __shared__ int s_av[MP_MAX_PLAYERS * 4];
+  __shared__ int s_av_all[RENDER_TEAMS][MP_MAX_PLAYERS * 4];
 
   const int tid = threadIdx.x;
-  const int first = blockIdx.x;
-  if (first >= S.B) return;
+  const int team = tid / TEAM_THREADS, ttid = tid % TEAM_THREADS;
+  uint8_t* s_team = smem + R.off_team0 + team * R.team_stride;
+  uint16_t* s_grid = reinterpret_cast<uint16_t*>(s_team + R.toff_grid);
+  uint16_t* s_rec = reinterpret_cast<uint16_t*>(s_team + R.toff_rec);
+  uint8_t* s_tile_base = s_team + R.toff_tile0;
+  const int tile_stride = R.toff_tile1 - R.toff_tile0;
+  int* s_av = s_av_all[team];
+  uint64_t* gbar = &bar[1 + team];
+
+  const int n_streams = gridDim.x * RENDER_TEAMS;
+  const int first = blockIdx.x * RENDER_TEAMS + team;
   if (tid == 0) {
-    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1);
+    for (int i = 0; i < 1 + RENDER_TEAMS; ++i) mbar_init(&bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(&bar[0], (uint32_t)R.atlas_bytes);
     bulk_load(s_atlas, T.atlas, (uint32_t)R.atlas_bytes, &bar[0]);
-    mbar_expect_tx(&bar[1], (uint32_t)R.grid_bytes);
-    bulk_load(s_grid_base, S.grid + (size_t)first * T.L * T.cells_pad, (uint32_t)R.grid_bytes, &bar[1]);
   }
-  for (int i = tid; i < (T.P + 1) * T.n_sprites; i += RENDER_THREADS) s_map[i] = T.sprite_map[i];
-  for (int i = tid; i < T.n_sprites; i += RENDER_THREADS) s_opaque[i] = T.sprite_opaque[i];
-#ifndef MP_DEBUG_NOFIX
-  __syncthreads();
-#endif
+  if (ttid == 0 && first < S.B) {
+    mbar_expect_tx(gbar, (uint32_t)R.grid_bytes);
+    bulk_load(s_grid, S.grid + (size_t)first * T.L * T.cells_pad, (uint32_t)R.grid_bytes, gbar);
+  }
+  for (int i = tid; i < (T.P + 1) * R.n_total; i += RENDER_THREADS) s_map[i] = T.sprite_map[i];
+  for (int i = tid; i < R.n_total; i += RENDER_THREADS) s_opaque[i] = T.sprite_opaque[i];
+  for (int i = tid; i < R.n_total * R.n_total; i += RENDER_THREADS) smem[R.off_pair + i] = T.sprite_pair[i];
+  __syncthreads();  // tables visible to every warp before the first cell pass
   mbar_wait(&bar[0], 0);
+  if (first >= S.B) return;
 
+  const int py = ttid & 7;  // TEAM_THREADS % 8 == 0: a thread always draws the same pixel row
   uint32_t tiles_done = 0;
   int it = 0;
-  for (int b = first; b < S.B; b += gridDim.x, ++it) {
-    const int gb = it & 1;
-    const uint16_t* s_grid = reinterpret_cast<const uint16_t*>(s_grid_base + gb * grid_stride);
-    // prefetch the next env's grid into the other buffer (its last reader finished an iteration ago)
-    const int nb = b + gridDim.x;
-    if (tid == 0 && nb < S.B) {
-      mbar_expect_tx(&bar[1 + (gb ^ 1)], (uint32_t)R.grid_bytes);
-      bulk_load(s_grid_base + (gb ^ 1) * grid_stride, S.grid + (size_t)nb * T.L * T.cells_pad, (uint32_t)R.grid_bytes, &bar[1 + (gb ^ 1)]);
-    }
-    if (tid < T.P * 4) s_av[tid] = S.avatar[(size_t)b * T.P * 4 + tid];
-    mbar_wait(&bar[1 + gb], (uint32_t)((it >> 1) & 1));
-    // Per-cell layer mask: top-down until a fully opaque sprite (everything below is hidden).
-    for (int c = tid; c < T.cells; c += RENDER_THREADS) {
-      uint32_t m = 0;
-      for (int l = T.L - 1; l >= 0; --l) {
+  for (int b = first; b < S.B; b += n_streams, ++it) {
+    if (ttid < T.P * 4) s_av[ttid] = S.avatar[(size_t)b * T.P * 4 + ttid];
+    mbar_wait(gbar, (uint32_t)(it & 1));
+    // ---- per-cell pass: flatten the layer stack, folding map sprites into pre-merged ones -------
+    for (int c = ttid; c < T.cells; c += TEAM_THREADS) {
+      int lo = 0;
+      for (int l = T.L - 1; l > 0; --l) {
         const int v = s_grid[l * T.cells_pad + c];
-        if (v) { m |= 1u << l; if (s_opaque[(v - 1) >> 2]) break; }
+        if (v && s_opaque[(v - 1) >> 2]) { lo = l; break; }
       }
-      s_mask[c] = (uint16_t)m;
+      uint16_t* r = s_rec + c * R.rec_stride;
+      int n = 0, cur = 0;
+      bool merging = true;
+      for (int l = lo; l < T.L; ++l) {
+        const int v = s_grid[l * T.cells_pad + c];
+        if (!v) continue;
+        if (cur == 0) { cur = v; continue; }
+        if (merging) {
+          const int m = s_pair[((cur - 1) >> 2) * R.n_total + ((v - 1) >> 2)];
+          if (m && (((cur - 1) ^ (v - 1)) & 3) == 0) { cur = 1 + m * 4 + ((v - 1) & 3); continue; }
+          merging = false;
+        }
+        r[1 + n++] = (uint16_t)cur;
+        cur = v;
+      }
+      if (cur) r[1 + n++] = (uint16_t)cur;
+      r[0] = (uint16_t)n;
     }
-    __syncthreads();
+    team_sync(team);
+    // the grid buffer is free again: prefetch the next env of this team
+    const int nb = b + n_streams;
+    if (ttid == 0 && nb < S.B) {
+      mbar_expect_tx(gbar, (uint32_t)R.grid_bytes);
+      bulk_load(s_grid, S.grid + (size_t)nb * T.L * T.cells_pad, (uint32_t)R.grid_bytes, gbar);
+    }
 
     const int n_tiles = ((flags & 2u) ? T.P : 0) + ((flags & 1u) ? R.n_bands : 0);
     for (int t = 0; t < n_tiles; ++t, ++tiles_done) {
-      const int tb = tiles_done & 1;
-      uint8_t* tile = s_tile_base + tb * tile_stride;
-      if (tid == 0) bulk_wait_read<1>();  // the store issued from this buffer two tiles ago has drained
-      __syncthreads();
+      uint8_t* tile = s_tile_base + (tiles_done & 1) * tile_stride;
+      if (ttid == 0) bulk_wait_read<1>();  // the store issued from this buffer two tiles ago has drained
+      team_sync(team);
       const bool is_player = (flags & 2u) && t < T.P;
       uint8_t* gdst; uint32_t gbytes;
       if (is_player) {
         const int p = t;
         const int ax = s_av[p * 4 + AV_X], ay = s_av[p * 4 + AV_Y], ao = s_av[p * 4 + AV_ORIENT], alive = s_av[p * 4 + AV_ALIVE];
-        const int16_t* map = s_map + p * T.n_sprites;
+        const int16_t* map = s_map + p * R.n_total;
         const int fdx = dir_dx(ao), fdy = dir_dy(ao), rdx = dir_dx((ao + 1) & 3), rdy = dir_dy((ao + 1) & 3);
         const int row_bytes = R.view_w * 24;
-        const int n_items = R.view_w * R.view_h * 8;
-        for (int i = tid; i < n_items; i += RENDER_THREADS) {
-          const int c = i >> 3, py = i & 7;
+        const int n_cells = R.view_w * R.view_h;
+        for (int c = ttid >> 3; c < n_cells; c += TEAM_THREADS / 8) {
           const int cy = (int)(((uint32_t)c * R.magic_view_w) >> 16), cx = c - cy * R.view_w;
           uint32_t px[8] = {0, 0, 0, 0, 0, 0, 0, 0};
           if (!alive) {
@@ -203,10 +235,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 2) k_render(Tables T, State S,
             const int dr = cx - T.view_l, df = T.view_f - cy;
             int wx = ax + rdx * dr + fdx * df, wy = ay + rdy * dr + fdy * df;
             if (!wrap_or_reject(T, wx, wy)) fixed_row(px, s_atlas, T.oob_sprite, py);
-            else {
-              const int cell = wy * T.W + wx;
-              compose_row(px, s_atlas, s_grid, map, s_opaque, T.cells_pad, cell, s_mask[cell], ao, py);
-            }
+            else compose_record(px, s_atlas, s_rec + (wy * T.W + wx) * R.rec_stride, map, s_opaque, ao, py);
           }
           store_row(tile + (cy * 8 + py) * row_bytes + cx * 24, px);
         }
@@ -216,32 +245,23 @@ __global__ void __launch_bounds__(RENDER_THREADS, 2) k_render(Tables T, State S,
         const int band = t - ((flags & 2u) ? T.P : 0);
         const int row0 = band * R.band_rows;
         const int rows = min(R.band_rows, T.H - row0);
-        const int16_t* map = s_map + T.P * T.n_sprites;
+        const int16_t* map = s_map + T.P * R.n_total;
         const int row_bytes = T.W * 24;
-        const int n_items = rows * T.W * 8;
-        for (int i = tid; i < n_items; i += RENDER_THREADS) {
-          const int c = i >> 3, py = i & 7;
+        const int n_cells = rows * T.W;
+        for (int c = ttid >> 3; c < n_cells; c += TEAM_THREADS / 8) {
           const int cy = (int)(((uint32_t)c * R.magic_world_w) >> 16), cx = c - cy * T.W;
-          const int cell = (row0 + cy) * T.W + cx;
           uint32_t px[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#ifdef MP_DEBUG_RENDER
-          if (b == 0 && py == 0 && (int)(flags >> 8) == cell) {
-            printf("dbg cell %d mask %x opaque5 %d L %d:", cell, (unsigned)s_mask[cell], (int)s_opaque[5], T.L);
-            for (int l = 0; l < T.L; ++l) printf(" %d", (int)s_grid[l * T.cells_pad + cell]);
-            printf("\n");
-          }
-#endif
-          compose_row(px, s_atlas, s_grid, map, s_opaque, T.cells_pad, cell, s_mask[cell], 0, py);
+          compose_record(px, s_atlas, s_rec + ((row0 + cy) * T.W + cx) * R.rec_stride, map, s_opaque, 0, py);
           store_row(tile + (cy * 8 + py) * row_bytes + cx * 24, px);
         }
         gdst = S.world_rgb + (size_t)b * R.world_bytes + (size_t)row0 * 8 * row_bytes;
         gbytes = (uint32_t)(rows * 8 * row_bytes);
       }
       fence_async_smem();  // make this thread's tile writes visible to the async (TMA) proxy
-      __syncthreads();
-      if (tid == 0) bulk_store(gdst, tile, gbytes);
+      team_sync(team);
+      if (ttid == 0) bulk_store(gdst, tile, gbytes);
     }
-    __syncthreads();  // all readers of s_grid / s_mask / s_av are done before the next env overwrites them
+    team_sync(team);  // all readers of s_rec / s_av are done before the next env overwrites them
   }
-  if (tid == 0) bulk_wait_read<0>();
+  if (ttid == 0) bulk_wait_read<0>();
 }
