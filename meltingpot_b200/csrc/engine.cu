@@ -350,11 +350,8 @@ int build_plan(mp_engine* E) {
   RenderPlan& R = E->R;
   R.view_w = T.view_l + T.view_r + 1; R.view_h = T.view_f + T.view_b + 1;
   R.player_bytes = R.view_w * R.view_h * 192;
-  const int cell_row_bytes = T.W * 192;
-  R.band_rows = std::max(1, R.player_bytes / cell_row_bytes);
-  R.n_bands = (T.H + R.band_rows - 1) / R.band_rows;
-  R.world_bytes = T.H * cell_row_bytes;
-  R.tile_bytes = round_up(std::max(R.player_bytes, R.band_rows * cell_row_bytes), 128);
+  R.world_bytes = T.H * T.W * 192;
+  R.stage_bytes = round_up(std::max(2 * R.view_w * 192, T.W * 192), 128);
   R.grid_bytes = T.L * T.cells_pad * 2;
   R.n_total = E->n_total;
   R.atlas_bytes = R.n_total * 1024;
@@ -369,8 +366,7 @@ int build_plan(mp_engine* E) {
   int toff = 0;
   R.toff_grid = toff; toff += round_up(R.grid_bytes, 128);
   R.toff_rec = toff; toff += round_up(T.cells * R.rec_stride * 2, 128);
-  R.toff_tile0 = toff; toff += R.tile_bytes;
-  R.toff_tile1 = toff; toff += R.tile_bytes;
+  R.toff_stage = toff; toff += (TEAM_THREADS / 32) * R.stage_bytes;
   R.team_stride = toff;
   R.smem_bytes = R.off_team0 + RENDER_TEAMS * R.team_stride;
   if (R.smem_bytes > 227 * 1024) return fail(MP_E_UNSUPPORTED, "render kernel needs %d B of shared memory (> 227 KB)", R.smem_bytes);

@@ -14,9 +14,10 @@
 //   2. a per-cell pass flattens every cell's layer stack into a short record, folding the opaque
 //      bottom sprite and the map sprites stacked on it into one pre-merged opaque sprite
 //      (merged on the host with exactly the compositing arithmetic, so results stay bit-exact);
-//   3. images are composed tile by tile in shared memory (8 pixels = 24 bytes per thread-item) and
-//      leave through cp.async.bulk shared->global stores, double buffered, so every observation
-//      byte is written once, fully coalesced, by the copy engine.
+//   3. warps pull "cell-row" items (8 pixel rows of one image), compose them in a warp-private
+//      staging buffer (8 pixels = 24 bytes per lane-item) and hand the buffer to cp.async.bulk
+//      shared->global stores, so every observation byte is written once, fully coalesced, by the
+//      copy engine, with no block-wide barrier on the way.
 #pragma once
 
 #include <cstdio>
@@ -30,9 +31,7 @@
 struct RenderPlan {  // host-computed constants of the tiling
   int view_w, view_h;        // cells
   int player_bytes;          // per-player image
-  int band_rows, n_bands;    // WORLD.RGB is cut into bands of `band_rows` cell rows
   int world_bytes;
-  int tile_bytes;            // shared-memory tile buffer (>= player_bytes, >= band bytes)
   int grid_bytes;            // L * cells_pad * 2
   int atlas_bytes;           // n_total sprites * 1024
   int n_total;               // atlas sprites including pre-merged ones
@@ -40,7 +39,8 @@ struct RenderPlan {  // host-computed constants of the tiling
   uint32_t magic_view_w, magic_world_w;  // q = (c * magic) >> 16 == c / w for c < 4096
   // shared memory offsets
   int off_atlas, off_pair, off_map, off_team0, team_stride;
-  int toff_grid, toff_rec, toff_tile0, toff_tile1;  // within a team's region
+  int toff_grid, toff_rec, toff_stage;  // within a team's region
+  int stage_bytes;                      // warp-private staging buffer (one world cell-row or two player cell-rows)
   int smem_bytes;
 };
 
@@ -132,6 +132,26 @@ __device__ __forceinline__ void store_row(uint8_t* dst, const uint32_t px[8]) {
   d[0] = a; d[1] = b; d[2] = c;
 }
 
+// Composes one (cell, pixel row) item: fast path for cells flattened to a single opaque sprite.
+__device__ __forceinline__ void compose_cell(uint32_t px[8], const uint8_t* __restrict__ s_atlas, const uint16_t* __restrict__ rec,
+                                             const int16_t* __restrict__ s_map, const uint8_t* __restrict__ opaque,
+                                             int viewer_orient, int py) {
+  const int h = rec[0];
+  if (h & 0x8000) {
+    const int v = h & 0x7fff;  // sprite * 4 + orientation
+    const uint8_t* t = s_atlas + ((v & ~3) | (((v & 3) - viewer_orient) & 3)) * 256 + py * 16;
+    const uint4 lo = *reinterpret_cast<const uint4*>(t);
+    const uint4 hi = *reinterpret_cast<const uint4*>(t + 128);
+    px[0] = lo.x; px[1] = lo.y; px[2] = lo.z; px[3] = lo.w; px[4] = hi.x; px[5] = hi.y; px[6] = hi.z; px[7] = hi.w;
+  } else {
+    compose_record(px, s_atlas, rec, s_map, opaque, viewer_orient, py);
+  }
+}
+
+// Work decomposition: an env is rendered by one team; after the per-cell pass its warps pull
+// "cell-row" items (one row of view cells = 8 pixel rows of one image) from a shared counter,
+// compose them into a warp-private staging buffer and hand that buffer to the TMA store engine.
+// Only three team barriers per env; everything else is warp-local.
 __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S, RenderPlan R, uint32_t flags) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // [0] atlas, [1 + team] grid
@@ -140,14 +160,15 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
   int16_t* s_map = reinterpret_cast<int16_t*>(smem + R.off_map);      // [P+1][n_total]
   __shared__ uint8_t s_opaque[256];
   __shared__ int s_av_all[RENDER_TEAMS][MP_MAX_PLAYERS * 4];
+  __shared__ int s_next_item[RENDER_TEAMS];
 
   const int tid = threadIdx.x;
   const int team = tid / TEAM_THREADS, ttid = tid % TEAM_THREADS;
+  const int lane = tid & 31, twarp = ttid >> 5;
   uint8_t* s_team = smem + R.off_team0 + team * R.team_stride;
   uint16_t* s_grid = reinterpret_cast<uint16_t*>(s_team + R.toff_grid);
   uint16_t* s_rec = reinterpret_cast<uint16_t*>(s_team + R.toff_rec);
-  uint8_t* s_tile_base = s_team + R.toff_tile0;
-  const int tile_stride = R.toff_tile1 - R.toff_tile0;
+  uint8_t* s_stage = s_team + R.toff_stage + twarp * R.stage_bytes;  // warp-private
   int* s_av = s_av_all[team];
   uint64_t* gbar = &bar[1 + team];
 
@@ -157,6 +178,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
     for (int i = 0; i < 1 + RENDER_TEAMS; ++i) mbar_init(&bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (ttid == 0) s_next_item[team] = 0;
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(&bar[0], (uint32_t)R.atlas_bytes);
@@ -173,8 +195,13 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
   mbar_wait(&bar[0], 0);
   if (first >= S.B) return;
 
-  const int py = ttid & 7;  // TEAM_THREADS % 8 == 0: a thread always draws the same pixel row
-  uint32_t tiles_done = 0;
+  const int py = lane & 7, cg = lane >> 3;  // a lane draws pixel row py of cells cg, cg+4, ...
+  const int n_player_items = (flags & 2u) ? T.P * R.view_h : 0;
+  const int n_items = n_player_items + ((flags & 1u) ? T.H : 0);
+  const int prow_bytes = R.view_w * 24, wrow_bytes = T.W * 24;
+  const int pitem_bytes = prow_bytes * 8, witem_bytes = wrow_bytes * 8;
+  uint32_t slot = 0;  // alternates between the two player-row slots of the staging buffer
+  bool after_world = false;
   int it = 0;
   for (int b = first; b < S.B; b += n_streams, ++it) {
     if (ttid < T.P * 4) s_av[ttid] = S.avatar[(size_t)b * T.P * 4 + ttid];
@@ -202,66 +229,69 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
         cur = v;
       }
       if (cur) r[1 + n++] = (uint16_t)cur;
-      r[0] = (uint16_t)n;
+      if (n == 1 && s_opaque[(cur - 1) >> 2]) r[0] = (uint16_t)(0x8000 | (cur - 1));  // single opaque sprite: fast path
+      else r[0] = (uint16_t)n;
     }
-    team_sync(team);
-    // the grid buffer is free again: prefetch the next env of this team
+    team_sync(team);  // records complete; the grid buffer is free again
     const int nb = b + n_streams;
     if (ttid == 0 && nb < S.B) {
       mbar_expect_tx(gbar, (uint32_t)R.grid_bytes);
       bulk_load(s_grid, S.grid + (size_t)nb * T.L * T.cells_pad, (uint32_t)R.grid_bytes, gbar);
     }
 
-    const int n_tiles = ((flags & 2u) ? T.P : 0) + ((flags & 1u) ? R.n_bands : 0);
-    for (int t = 0; t < n_tiles; ++t, ++tiles_done) {
-      uint8_t* tile = s_tile_base + (tiles_done & 1) * tile_stride;
-      if (ttid == 0) bulk_wait_read<1>();  // the store issued from this buffer two tiles ago has drained
-      team_sync(team);
-      const bool is_player = (flags & 2u) && t < T.P;
-      uint8_t* gdst; uint32_t gbytes;
-      if (is_player) {
-        const int p = t;
+    // ---- cell-row items, pulled by warps ------------------------------------------------------------
+    for (;;) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(&s_next_item[team], 1);
+      item = __shfl_sync(MP_FULL, item, 0);
+      if (item >= n_items) break;
+      if (item < n_player_items) {
+        const int p = item / R.view_h, cy = item - p * R.view_h;
+        uint8_t* buf = s_stage + (slot & 1) * pitem_bytes;
+        ++slot;
+        if (lane == 0) { if (after_world) bulk_wait_read<0>(); else bulk_wait_read<1>(); }  // the slot's last store has drained
+        after_world = false;
+        __syncwarp();
         const int ax = s_av[p * 4 + AV_X], ay = s_av[p * 4 + AV_Y], ao = s_av[p * 4 + AV_ORIENT], alive = s_av[p * 4 + AV_ALIVE];
         const int16_t* map = s_map + p * R.n_total;
         const int fdx = dir_dx(ao), fdy = dir_dy(ao), rdx = dir_dx((ao + 1) & 3), rdy = dir_dy((ao + 1) & 3);
-        const int row_bytes = R.view_w * 24;
-        const int n_cells = R.view_w * R.view_h;
-        for (int c = ttid >> 3; c < n_cells; c += TEAM_THREADS / 8) {
-          const int cy = (int)(((uint32_t)c * R.magic_view_w) >> 16), cx = c - cy * R.view_w;
+        const int df = T.view_f - cy;
+        for (int cx = cg; cx < R.view_w; cx += 4) {
           uint32_t px[8] = {0, 0, 0, 0, 0, 0, 0, 0};
           if (!alive) {
             fixed_row(px, s_atlas, T.oov_sprite, py);  // policy A.13
           } else {
-            const int dr = cx - T.view_l, df = T.view_f - cy;
+            const int dr = cx - T.view_l;
             int wx = ax + rdx * dr + fdx * df, wy = ay + rdy * dr + fdy * df;
             if (!wrap_or_reject(T, wx, wy)) fixed_row(px, s_atlas, T.oob_sprite, py);
-            else compose_record(px, s_atlas, s_rec + (wy * T.W + wx) * R.rec_stride, map, s_opaque, ao, py);
+            else compose_cell(px, s_atlas, s_rec + (wy * T.W + wx) * R.rec_stride, map, s_opaque, ao, py);
           }
-          store_row(tile + (cy * 8 + py) * row_bytes + cx * 24, px);
+          store_row(buf + py * prow_bytes + cx * 24, px);
         }
-        gdst = S.rgb + ((size_t)b * T.P + p) * R.player_bytes;
-        gbytes = (uint32_t)R.player_bytes;
+        fence_async_smem();  // make this lane's writes visible to the async (TMA) proxy
+        __syncwarp();
+        if (lane == 0) bulk_store(S.rgb + ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * pitem_bytes, buf, (uint32_t)pitem_bytes);
       } else {
-        const int band = t - ((flags & 2u) ? T.P : 0);
-        const int row0 = band * R.band_rows;
-        const int rows = min(R.band_rows, T.H - row0);
+        const int wy = item - n_player_items;
+        uint8_t* buf = s_stage;  // a world row uses the whole staging buffer
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
         const int16_t* map = s_map + T.P * R.n_total;
-        const int row_bytes = T.W * 24;
-        const int n_cells = rows * T.W;
-        for (int c = ttid >> 3; c < n_cells; c += TEAM_THREADS / 8) {
-          const int cy = (int)(((uint32_t)c * R.magic_world_w) >> 16), cx = c - cy * T.W;
+        for (int cx = cg; cx < T.W; cx += 4) {
           uint32_t px[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          compose_record(px, s_atlas, s_rec + ((row0 + cy) * T.W + cx) * R.rec_stride, map, s_opaque, 0, py);
-          store_row(tile + (cy * 8 + py) * row_bytes + cx * 24, px);
+          compose_cell(px, s_atlas, s_rec + (wy * T.W + cx) * R.rec_stride, map, s_opaque, 0, py);
+          store_row(buf + py * wrow_bytes + cx * 24, px);
         }
-        gdst = S.world_rgb + (size_t)b * R.world_bytes + (size_t)row0 * 8 * row_bytes;
-        gbytes = (uint32_t)(rows * 8 * row_bytes);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wy * witem_bytes, buf, (uint32_t)witem_bytes);
+        after_world = true;  // both player slots overlap the row just handed to the store engine
+        slot = 0;
       }
-      fence_async_smem();  // make this thread's tile writes visible to the async (TMA) proxy
-      team_sync(team);
-      if (ttid == 0) bulk_store(gdst, tile, gbytes);
     }
-    team_sync(team);  // all readers of s_rec / s_av are done before the next env overwrites them
+    team_sync(team);  // every warp is done with s_rec / s_av
+    if (ttid == 0) s_next_item[team] = 0;
+    // (the reset is ordered before the next env's item loop by the team barrier after its cell pass)
   }
-  if (ttid == 0) bulk_wait_read<0>();
+  if (lane == 0) bulk_wait_read<0>();
 }
