@@ -96,6 +96,7 @@ struct mp_engine {
   uint64_t launches = 0;
   int sm_count = 0;
   size_t step_smem = 0;
+  void (*render_fn)(Tables, State, RenderPlan, uint32_t) = nullptr;
   uint64_t algo_bytes = 0, render_bytes = 0;
 
   template <typename T>
@@ -351,13 +352,12 @@ int build_plan(mp_engine* E) {
   R.view_w = T.view_l + T.view_r + 1; R.view_h = T.view_f + T.view_b + 1;
   R.player_bytes = R.view_w * R.view_h * 192;
   R.world_bytes = T.H * T.W * 192;
-  R.stage_bytes = round_up(std::max(2 * R.view_w * 192, T.W * 192), 128);
+  R.stage_bytes = 2 * round_up(std::max(R.view_w * 192, T.W * 48), 128);
   R.grid_bytes = T.L * T.cells_pad * 2;
   R.n_total = E->n_total;
   R.atlas_bytes = R.n_total * 1024;
   R.rec_stride = T.L + 1;
-  R.magic_view_w = (65536u + R.view_w - 1) / R.view_w;
-  R.magic_world_w = (65536u + T.W - 1) / T.W;
+  R.magic_view_h = (65536u + R.view_h - 1) / R.view_h;
   int off = 128;  // mbarriers
   R.off_atlas = off; off += round_up(R.atlas_bytes, 128);
   R.off_pair = off; off += round_up(R.n_total * R.n_total, 128);
@@ -384,7 +384,7 @@ int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int 
 int launch_render(mp_engine* E, cudaStream_t st) {
   if (!(E->flags & (MP_FLAG_RENDER_WORLD | MP_FLAG_RENDER_PLAYERS))) return MP_OK;
   const int blocks = std::min((E->B + RENDER_TEAMS - 1) / RENDER_TEAMS, E->sm_count);
-  k_render<<<blocks, RENDER_THREADS, E->R.smem_bytes, st>>>(E->T, E->S, E->R, E->flags);
+  E->render_fn<<<blocks, RENDER_THREADS, E->R.smem_bytes, st>>>(E->T, E->S, E->R, E->flags);
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;
@@ -452,7 +452,14 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
     if (ce != cudaSuccess) { mp_destroy(E); return fail(MP_E_CUDA, "cudaMemcpy(env) failed: %s", cudaGetErrorString(ce)); }
   }
   E->step_smem = warp_scratch_bytes(T);
-  cudaError_t ce = cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, E->R.smem_bytes);
+  {  // cells per lane per strip: ceil(view_w / 4) for player rows, ceil(W / 16) for world quarter-rows
+    const int ncp = (E->R.view_w + 3) / 4, ncw = (T.W + 15) / 16;
+    if (ncp <= 3 && ncw <= 2) E->render_fn = k_render<3, 2>;
+    else if (ncp <= 4 && ncw <= 2) E->render_fn = k_render<4, 2>;
+    else if (ncp <= 4 && ncw <= 4) E->render_fn = k_render<4, 4>;
+    else { mp_destroy(E); return fail(MP_E_UNSUPPORTED, "view of %d cells / map of %d cells wide (max 16 / 64)", E->R.view_w, T.W); }
+  }
+  cudaError_t ce = cudaFuncSetAttribute(E->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E->R.smem_bytes);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_clean_up, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
   if (ce != cudaSuccess) { mp_destroy(E); return fail(MP_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)); }
   mp_buffers& bf = E->buffers;

@@ -36,11 +36,11 @@ struct RenderPlan {  // host-computed constants of the tiling
   int atlas_bytes;           // n_total sprites * 1024
   int n_total;               // atlas sprites including pre-merged ones
   int rec_stride;            // u16 per cell record: count + up to L entries
-  uint32_t magic_view_w, magic_world_w;  // q = (c * magic) >> 16 == c / w for c < 4096
+  uint32_t magic_view_h;     // p = (item * magic) >> 16 == item / view_h for item < 4096
   // shared memory offsets
   int off_atlas, off_pair, off_map, off_team0, team_stride;
   int toff_grid, toff_rec, toff_stage;  // within a team's region
-  int stage_bytes;                      // warp-private staging buffer (one world cell-row or two player cell-rows)
+  int stage_bytes;                      // warp-private staging buffer: two slots, each one player cell-row or half a world cell-row
   int smem_bytes;
 };
 
@@ -132,26 +132,29 @@ __device__ __forceinline__ void store_row(uint8_t* dst, const uint32_t px[8]) {
   d[0] = a; d[1] = b; d[2] = c;
 }
 
-// Composes one (cell, pixel row) item: fast path for cells flattened to a single opaque sprite.
-__device__ __forceinline__ void compose_cell(uint32_t px[8], const uint8_t* __restrict__ s_atlas, const uint16_t* __restrict__ rec,
-                                             const int16_t* __restrict__ s_map, const uint8_t* __restrict__ opaque,
-                                             int viewer_orient, int py) {
-  const int h = rec[0];
-  if (h & 0x8000) {
-    const int v = h & 0x7fff;  // sprite * 4 + orientation
-    const uint8_t* t = s_atlas + ((v & ~3) | (((v & 3) - viewer_orient) & 3)) * 256 + py * 16;
-    const uint4 lo = *reinterpret_cast<const uint4*>(t);
-    const uint4 hi = *reinterpret_cast<const uint4*>(t + 128);
-    px[0] = lo.x; px[1] = lo.y; px[2] = lo.z; px[3] = lo.w; px[4] = hi.x; px[5] = hi.y; px[6] = hi.z; px[7] = hi.w;
-  } else {
-    compose_record(px, s_atlas, rec, s_map, opaque, viewer_orient, py);
-  }
+// Header of a flattened cell record: bit 15 set = the cell is a single opaque sprite and the low
+// bits are sprite * 4 + orientation (fast path); otherwise the number of entries that follow.
+#define REC_FAST 0x8000
+
+// Loads pixel row `py` of the sprite variant selected by a fast-path header.
+__device__ __forceinline__ void fast_row(uint32_t px[8], const uint8_t* __restrict__ s_atlas, int h, int viewer_orient, int py) {
+  const int v = h & 0x7fff;
+  const uint8_t* t = s_atlas + ((v & ~3) | (((v & 3) - viewer_orient) & 3)) * 256 + py * 16;
+  const uint4 lo = *reinterpret_cast<const uint4*>(t);
+  const uint4 hi = *reinterpret_cast<const uint4*>(t + 128);
+  px[0] = lo.x; px[1] = lo.y; px[2] = lo.z; px[3] = lo.w; px[4] = hi.x; px[5] = hi.y; px[6] = hi.z; px[7] = hi.w;
 }
 
+struct ViewerInfo {  // per player, refreshed once per env
+  int ax, ay, ao, alive, fdx, fdy, rdx, rdy;
+};
+
 // Work decomposition: an env is rendered by one team; after the per-cell pass its warps pull
-// "cell-row" items (one row of view cells = 8 pixel rows of one image) from a shared counter,
-// compose them into a warp-private staging buffer and hand that buffer to the TMA store engine.
-// Only three team barriers per env; everything else is warp-local.
+// strip items from a shared counter -- one row of view cells (8 pixel rows) of a player image, or
+// a quarter cell row (2 pixel rows) of WORLD.RGB -- compose them into a warp-private staging slot and
+// hand the slot to the TMA store engine. Three team barriers per env; everything else is warp-local.
+// Each lane handles NC cells per strip with the loads of all NC cells issued before any is packed.
+template <int NCP, int NCW>
 __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S, RenderPlan R, uint32_t flags) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // [0] atlas, [1 + team] grid
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
   const uint8_t* s_pair = smem + R.off_pair;                          // [n_total][n_total] merged sprite or 0
   int16_t* s_map = reinterpret_cast<int16_t*>(smem + R.off_map);      // [P+1][n_total]
   __shared__ uint8_t s_opaque[256];
-  __shared__ int s_av_all[RENDER_TEAMS][MP_MAX_PLAYERS * 4];
+  __shared__ ViewerInfo s_view_all[RENDER_TEAMS][MP_MAX_PLAYERS];
   __shared__ int s_next_item[RENDER_TEAMS];
 
   const int tid = threadIdx.x;
@@ -168,8 +171,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
   uint8_t* s_team = smem + R.off_team0 + team * R.team_stride;
   uint16_t* s_grid = reinterpret_cast<uint16_t*>(s_team + R.toff_grid);
   uint16_t* s_rec = reinterpret_cast<uint16_t*>(s_team + R.toff_rec);
-  uint8_t* s_stage = s_team + R.toff_stage + twarp * R.stage_bytes;  // warp-private
-  int* s_av = s_av_all[team];
+  uint8_t* s_stage = s_team + R.toff_stage + twarp * R.stage_bytes;  // warp-private, two slots
+  ViewerInfo* s_view = s_view_all[team];
   uint64_t* gbar = &bar[1 + team];
 
   const int n_streams = gridDim.x * RENDER_TEAMS;
@@ -195,16 +198,22 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
   mbar_wait(&bar[0], 0);
   if (first >= S.B) return;
 
-  const int py = lane & 7, cg = lane >> 3;  // a lane draws pixel row py of cells cg, cg+4, ...
   const int n_player_items = (flags & 2u) ? T.P * R.view_h : 0;
-  const int n_items = n_player_items + ((flags & 1u) ? T.H : 0);
+  const int n_items = n_player_items + ((flags & 1u) ? 4 * T.H : 0);
   const int prow_bytes = R.view_w * 24, wrow_bytes = T.W * 24;
-  const int pitem_bytes = prow_bytes * 8, witem_bytes = wrow_bytes * 8;
-  uint32_t slot = 0;  // alternates between the two player-row slots of the staging buffer
-  bool after_world = false;
+  const int pitem_bytes = prow_bytes * 8, witem_bytes = wrow_bytes * 2;
+  const int slot_bytes = R.stage_bytes >> 1;
+  const int h_oob = REC_FAST | (T.oob_sprite * 4), h_oov = REC_FAST | (T.oov_sprite * 4);
+  uint32_t slot = 0;
   int it = 0;
   for (int b = first; b < S.B; b += n_streams, ++it) {
-    if (ttid < T.P * 4) s_av[ttid] = S.avatar[(size_t)b * T.P * 4 + ttid];
+    if (ttid < T.P) {
+      const int4 a = *reinterpret_cast<const int4*>(S.avatar + ((size_t)b * T.P + ttid) * 4);
+      ViewerInfo vi;
+      vi.ax = a.x; vi.ay = a.y; vi.ao = a.z; vi.alive = a.w;
+      vi.fdx = dir_dx(a.z); vi.fdy = dir_dy(a.z); vi.rdx = dir_dx((a.z + 1) & 3); vi.rdy = dir_dy((a.z + 1) & 3);
+      s_view[ttid] = vi;
+    }
     mbar_wait(gbar, (uint32_t)(it & 1));
     // ---- per-cell pass: flatten the layer stack, folding map sprites into pre-merged ones -------
     for (int c = ttid; c < T.cells; c += TEAM_THREADS) {
@@ -229,7 +238,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
         cur = v;
       }
       if (cur) r[1 + n++] = (uint16_t)cur;
-      if (n == 1 && s_opaque[(cur - 1) >> 2]) r[0] = (uint16_t)(0x8000 | (cur - 1));  // single opaque sprite: fast path
+      if (n == 1 && s_opaque[(cur - 1) >> 2]) r[0] = (uint16_t)(REC_FAST | (cur - 1));
       else r[0] = (uint16_t)n;
     }
     team_sync(team);  // records complete; the grid buffer is free again
@@ -239,57 +248,89 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
       bulk_load(s_grid, S.grid + (size_t)nb * T.L * T.cells_pad, (uint32_t)R.grid_bytes, gbar);
     }
 
-    // ---- cell-row items, pulled by warps ------------------------------------------------------------
+    // ---- strip items, pulled by warps -------------------------------------------------------------
     for (;;) {
       int item = 0;
       if (lane == 0) item = atomicAdd(&s_next_item[team], 1);
       item = __shfl_sync(MP_FULL, item, 0);
       if (item >= n_items) break;
+      uint8_t* buf = s_stage + (slot & 1) * slot_bytes;
+      ++slot;
+      if (lane == 0) bulk_wait_read<1>();  // the store that last used this slot has drained
+      __syncwarp();
       if (item < n_player_items) {
-        const int p = item / R.view_h, cy = item - p * R.view_h;
-        uint8_t* buf = s_stage + (slot & 1) * pitem_bytes;
-        ++slot;
-        if (lane == 0) { if (after_world) bulk_wait_read<0>(); else bulk_wait_read<1>(); }  // the slot's last store has drained
-        after_world = false;
-        __syncwarp();
-        const int ax = s_av[p * 4 + AV_X], ay = s_av[p * 4 + AV_Y], ao = s_av[p * 4 + AV_ORIENT], alive = s_av[p * 4 + AV_ALIVE];
+        const int p = (int)(((uint32_t)item * R.magic_view_h) >> 16), cy = item - p * R.view_h;
+        const ViewerInfo vi = s_view[p];
         const int16_t* map = s_map + p * R.n_total;
-        const int fdx = dir_dx(ao), fdy = dir_dy(ao), rdx = dir_dx((ao + 1) & 3), rdy = dir_dy((ao + 1) & 3);
+        const int py = lane & 7, cg = lane >> 3;
         const int df = T.view_f - cy;
-        for (int cx = cg; cx < R.view_w; cx += 4) {
-          uint32_t px[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          if (!alive) {
-            fixed_row(px, s_atlas, T.oov_sprite, py);  // policy A.13
-          } else {
-            const int dr = cx - T.view_l;
-            int wx = ax + rdx * dr + fdx * df, wy = ay + rdy * dr + fdy * df;
-            if (!wrap_or_reject(T, wx, wy)) fixed_row(px, s_atlas, T.oob_sprite, py);
-            else compose_cell(px, s_atlas, s_rec + (wy * T.W + wx) * R.rec_stride, map, s_opaque, ao, py);
+        const int bx = vi.ax + vi.fdx * df - vi.rdx * T.view_l, by = vi.ay + vi.fdy * df - vi.rdy * T.view_l;
+        int hdr[NCP];
+        const uint16_t* rec[NCP];
+        uint32_t px[NCP][8];
+        if (!(flags & 16u)) {  // (bit 4: debug / ceiling measurement -- issue the stores without composing)
+#pragma unroll
+        for (int i = 0; i < NCP; ++i) {  // headers of all my cells first ...
+          const int cx = cg + 4 * i;
+          int wx = bx + vi.rdx * cx, wy = by + vi.rdy * cx;
+          const bool inb = wrap_or_reject(T, wx, wy);
+          rec[i] = s_rec + (inb ? (wy * T.W + wx) : 0) * R.rec_stride;
+          const int h = rec[i][0];
+          hdr[i] = !vi.alive ? (h_oov | vi.ao) : (inb ? h : (h_oob | vi.ao));  // policy A.13
+        }
+#pragma unroll
+        for (int i = 0; i < NCP; ++i) {  // ... then their sprite rows ...
+          if (hdr[i] & REC_FAST) fast_row(px[i], s_atlas, hdr[i], vi.ao, py);
+          else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) px[i][k] = 0;
+            compose_record(px[i], s_atlas, rec[i], map, s_opaque, vi.ao, py);
           }
-          store_row(buf + py * prow_bytes + cx * 24, px);
+        }
+#pragma unroll
+        for (int i = 0; i < NCP; ++i) {  // ... then pack and stage
+          const int cx = cg + 4 * i;
+          if (cx < R.view_w) store_row(buf + py * prow_bytes + cx * 24, px[i]);
+        }
         }
         fence_async_smem();  // make this lane's writes visible to the async (TMA) proxy
         __syncwarp();
         if (lane == 0) bulk_store(S.rgb + ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * pitem_bytes, buf, (uint32_t)pitem_bytes);
       } else {
-        const int wy = item - n_player_items;
-        uint8_t* buf = s_stage;  // a world row uses the whole staging buffer
-        if (lane == 0) bulk_wait_read<0>();
-        __syncwarp();
+        const int wi = item - n_player_items, wy = wi >> 2;
+        const int py = ((wi & 3) << 1) | (lane & 1), cg = lane >> 1;
         const int16_t* map = s_map + T.P * R.n_total;
-        for (int cx = cg; cx < T.W; cx += 4) {
-          uint32_t px[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          compose_cell(px, s_atlas, s_rec + (wy * T.W + cx) * R.rec_stride, map, s_opaque, 0, py);
-          store_row(buf + py * wrow_bytes + cx * 24, px);
+        const uint16_t* rowrec = s_rec + wy * T.W * R.rec_stride;
+        int hdr[NCW];
+        uint32_t px[NCW][8];
+        if (!(flags & 16u)) {
+#pragma unroll
+        for (int i = 0; i < NCW; ++i) {
+          const int cx = min(cg + 16 * i, T.W - 1);
+          hdr[i] = rowrec[cx * R.rec_stride];
+        }
+#pragma unroll
+        for (int i = 0; i < NCW; ++i) {
+          const int cx = min(cg + 16 * i, T.W - 1);
+          if (hdr[i] & REC_FAST) fast_row(px[i], s_atlas, hdr[i], 0, py);
+          else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) px[i][k] = 0;
+            compose_record(px[i], s_atlas, rowrec + cx * R.rec_stride, map, s_opaque, 0, py);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NCW; ++i) {
+          const int cx = cg + 16 * i;
+          if (cx < T.W) store_row(buf + (py & 1) * wrow_bytes + cx * 24, px[i]);
+        }
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wy * witem_bytes, buf, (uint32_t)witem_bytes);
-        after_world = true;  // both player slots overlap the row just handed to the store engine
-        slot = 0;
+        if (lane == 0) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wi * witem_bytes, buf, (uint32_t)witem_bytes);
       }
     }
-    team_sync(team);  // every warp is done with s_rec / s_av
+    team_sync(team);  // every warp is done with s_rec / s_view
     if (ttid == 0) s_next_item[team] = 0;
     // (the reset is ordered before the next env's item loop by the team barrier after its cell pass)
   }
