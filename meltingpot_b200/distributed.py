@@ -1,0 +1,87 @@
+"""Env-instance data parallelism: shard envs over ranks, gather the stacked scalar timestep.
+
+Env instances never interact (each `dmlab2d.Lab2d` is an isolated world,
+`/root/reference/meltingpot/utils/substrates/builder.py:179-187`), so the hot path itself needs
+no collective: rank r simply steps envs [base, base + count). Env b's RNG key is
+`seed + b` with b the GLOBAL env index, so results do not depend on the number of ranks.
+The only exchange is returning one stacked tensor per scalar timestep field to every rank
+(an all-gather over NCCL/NVLink, or gloo in the CPU tests); stacking the RGB observations is
+optional because it is NVLink-bound.
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+
+def shard_envs(global_num_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
+  """Returns (env_index_base, count) of the contiguous shard owned by `rank`."""
+  if not 0 <= rank < world_size:
+    raise ValueError(f'rank {rank} outside world of {world_size}')
+  if global_num_envs % world_size:
+    raise ValueError(f'{global_num_envs} envs do not split evenly over {world_size} ranks')
+  count = global_num_envs // world_size
+  return rank * count, count
+
+
+def all_gather_stacked(tensor, group=None):
+  """Stacks equal-shaped per-rank tensors along dim 0 on every rank (rank order = env order)."""
+  import torch  # pylint: disable=g-import-not-at-top
+  import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+  world = dist.get_world_size(group)
+  tensor = tensor.contiguous()
+  out = torch.empty((world * tensor.shape[0],) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+  if dist.get_backend(group) == 'nccl':
+    dist.all_gather_into_tensor(out, tensor, group=group)
+  else:
+    chunks = list(out.chunk(world, dim=0))
+    dist.all_gather(chunks, tensor, group=group)
+  return out
+
+
+def gather_timestep_scalars(reward, discount, step_type, group=None):
+  """All-gathers (reward [b,P], discount [b], step_type [b]) into global [B,...] tensors.
+
+  The three fields travel in one float64 buffer so that a step costs a single collective.
+  """
+  import torch  # pylint: disable=g-import-not-at-top
+  b, p = reward.shape
+  packed = torch.empty((b, p + 2), dtype=torch.float64, device=reward.device)
+  packed[:, :p] = reward
+  packed[:, p] = discount
+  packed[:, p + 1] = step_type.to(torch.float64)
+  full = all_gather_stacked(packed, group)
+  return full[:, :p], full[:, p], full[:, p + 1].to(torch.int64)
+
+
+class ShardedSubstrate:
+  """One rank's shard of a globally indexed batch of env instances."""
+
+  def __init__(self, name: str, roles, global_num_envs: int, seed: int, device: Optional[int] = None,
+               world_rgb: bool = True, group=None):
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+    from meltingpot_b200 import substrate  # pylint: disable=g-import-not-at-top
+    self._group = group
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    self.env_index_base, self.local_num_envs = shard_envs(global_num_envs, rank, world)
+    self.global_num_envs = global_num_envs
+    if device is None:
+      import torch  # pylint: disable=g-import-not-at-top
+      device = torch.cuda.current_device()
+    self.local = substrate.build_batched(name, roles=roles, num_envs=self.local_num_envs, device=device, seed=seed,
+                                         env_index_base=self.env_index_base, world_rgb=world_rgb)
+
+  def reset(self):
+    return self.local.reset()
+
+  def step(self, local_actions):
+    return self.local.step(local_actions)
+
+  def gather_scalars(self, timestep):
+    return gather_timestep_scalars(timestep.reward, timestep.discount, timestep.step_type, self._group)
+
+  def gather_observation(self, timestep, key: str = 'RGB'):
+    return all_gather_stacked(timestep.observation[key], self._group)
+
+  def close(self):
+    self.local.close()

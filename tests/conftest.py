@@ -23,3 +23,9 @@ def oracle():
   from oracle import binding
   binding.build()
   return binding
+
+
+@pytest.fixture(scope='session')
+def clean_river_blob():
+  with open(os.path.join(ROOT, 'tests', 'golden', 'clean_up_clean_river__7p.mpb'), 'rb') as f:
+    return f.read()

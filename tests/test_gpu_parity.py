@@ -28,3 +28,88 @@ def test_clean_up_cleaning_policy_grows_and_eats_apples(clean_up_blob, oracle):
 def test_clean_up_sharding_invariance(clean_up_blob, oracle):
   # env b of a shard that starts at env_index_base behaves like global env base+b.
   parity.compare_rollout(clean_up_blob, oracle, num_envs=4, steps=40, seed=5, env_index_base=1000)
+
+
+def test_clean_up_clean_river_apples_grow_and_get_eaten(clean_river_blob, oracle):
+  # Variant map (tools/make_test_blobs.py): river starts clean, so AppleGrow / Edible are exercised.
+  stats = parity.compare_rollout(clean_river_blob, oracle, num_envs=12, steps=400, seed=9, pixels_every=5)
+  assert stats['eaten'] > 20 and stats['rewards'] > 20
+
+
+def test_clean_up_full_batch_size_invariants(clean_up_blob, oracle):
+  # BASELINE.json config 2 size: 4096 envs. A sample of envs is compared bit-for-bit with the oracle;
+  # the whole batch is checked through size-independent properties.
+  import torch
+  from meltingpot_b200 import engine
+  B = 4096
+  sample = [0, 1, 777, 2048, 4095]
+  parity.compare_rollout(clean_up_blob, oracle, num_envs=B, steps=60, seed=21, check_envs=sample, pixels_every=10)
+  eng = engine.Engine(clean_up_blob, B, seed=21)
+  eng.reset()
+  first = eng.world_rgb.clone()
+  # every env renders a full frame: no pixel of WORLD.RGB is left at the allocation's zero fill inside the walls
+  assert int((eng.world_rgb[:, 8:-8, 8:-8] == 0).all(dim=-1).sum()) == 0
+  # walls never change: the border ring is identical across envs and across steps
+  ring = eng.world_rgb[:, :8].clone()
+  assert bool((ring == ring[0]).all())
+  gen = torch.Generator(device='cuda').manual_seed(0)
+  for _ in range(30):
+    eng.step(torch.randint(0, 9, (B, 7), generator=gen, device='cuda', dtype=torch.int32))
+  assert bool((eng.world_rgb[:, :8] == ring).all())
+  assert bool((eng.step_type == 1).all()) and bool((eng.discount == 1.0).all())
+  assert bool((eng.reward >= 0).all())
+  # envs with different seeds diverge, identical seeds stay identical
+  assert not bool((eng.world_rgb == first).all())
+  twin = engine.Engine(clean_up_blob, 64, seed=21)
+  twin.reset()
+  gen = torch.Generator(device='cuda').manual_seed(0)
+  for _ in range(30):
+    a = torch.randint(0, 9, (B, 7), generator=gen, device='cuda', dtype=torch.int32)
+    twin.step(a[:64].contiguous())
+  assert bool((twin.rgb == eng.rgb[:64]).all()) and bool((twin.world_rgb == eng.world_rgb[:64]).all())
+
+
+def test_clean_up_episode_boundary_auto_reset(clean_up_blob, oracle):
+  # Runs past the first possible episode end (frame 1099) so LAST -> FIRST transitions are compared.
+  stats = parity.compare_rollout(clean_up_blob, oracle, num_envs=24, steps=1320, seed=300, pixels_every=97)
+  assert stats['lasts'] > 0
+
+
+def test_dm_env_substrate_api(clean_up_blob):
+  from meltingpot_b200 import shims, substrate
+  shims.install()
+  import dm_env
+  with substrate.build('clean_up', roles=('default',) * 7, env_seed=5) as env:
+    ts = env.reset()
+    assert ts.step_type == dm_env.StepType.FIRST and ts.discount == 0.0 and ts.reward == [0.0] * 7
+    assert len(ts.observation) == 7
+    keys = {'RGB', 'READY_TO_SHOOT', 'NUM_OTHERS_WHO_CLEANED_THIS_STEP', 'WORLD.RGB', 'COLLECTIVE_REWARD'}
+    assert set(ts.observation[0]) == keys
+    assert ts.observation[0]['WORLD.RGB'] is ts.observation[6]['WORLD.RGB']
+    # assert_step_matches_specs (meltingpot/testing/substrates.py:22-68)
+    for obs, spec in zip(ts.observation, env.observation_spec()):
+      for k, v in obs.items():
+        spec[k].validate(v)
+    actions = [spec.maximum for spec in env.action_spec()]
+    ts = env.step(actions)
+    assert ts.step_type == dm_env.StepType.MID and ts.discount == 1.0
+    for r, spec in zip(ts.reward, env.reward_spec()):
+      spec.validate(r)
+    env.discount_spec().validate(ts.discount)
+    with pytest.raises(ValueError):
+      env.step([0] * 6)
+    with pytest.raises(ValueError):
+      env.step([9] * 7)
+  # same env_seed => identical first frame (builder_test.py:47-70)
+  a = substrate.build('clean_up', roles=('default',) * 7, env_seed=5)
+  b = substrate.build('clean_up', roles=('default',) * 7, env_seed=6)
+  fa, fb = a.reset().observation[0]['WORLD.RGB'], b.reset().observation[0]['WORLD.RGB']
+  assert np.array_equal(fa, ts_first_world(5)) and not np.array_equal(fa, fb)
+  assert not np.array_equal(a.reset().observation[0]['WORLD.RGB'], fa)  # next episode differs
+  a.close(); b.close()
+
+
+def ts_first_world(seed):
+  from meltingpot_b200 import substrate
+  with substrate.build('clean_up', roles=('default',) * 7, env_seed=seed) as env:
+    return env.reset().observation[0]['WORLD.RGB']
