@@ -56,6 +56,7 @@ typedef struct mp_buffers {
   int32_t* avatar_state;    /* i32 [B][P][4] x, y, orientation, alive (debug / parity) */
   uint16_t* grid;           /* u16 [B][L][cells_padded] sprite grid (debug / parity) */
   int32_t grid_layers, grid_cells, grid_cells_padded;
+  double* timestep_packed;  /* f64 [B][P+2]: reward[0..P), discount, step type -- one buffer for the per-step all-gather */
 } mp_buffers;
 
 /* Replaces dmlab2d.Lab2d(...) + dmlab2d.Environment(...) (builder.py:182-187) for `num_envs`

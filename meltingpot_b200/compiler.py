@@ -340,6 +340,7 @@ class WorldModel:
     self.comps_d: List[List[float]] = []
     self.objects: List[List[int]] = []
     self.kind_names: List[str] = []
+    self._needs_grass: List[int] = []
     self.state_names: List[List[str]] = []
     kind_of: Dict[str, int] = {}
     self.avatar_objs: List[int] = []
@@ -368,6 +369,12 @@ class WorldModel:
         self.avatar_objs.append(oid)
     if len(self.avatar_objs) != self.num_players:
       raise ValueError('number of avatar objects != numPlayers')
+    for ci in self._needs_grass:  # DensityRegrow toggles the underlying grass (components.lua:181-193)
+      grass = [n for n in self.state_names if 'grass' in n and 'dessicated' in n]
+      if not grass:
+        raise ValueError('DensityRegrow needs a prefab with states grass/dessicated')
+      self.comps_i[ci][1 + 9] = grass[0].index('grass')
+      self.comps_i[ci][1 + 10] = grass[0].index('dessicated')
     self.world_sprite_map = sim.get('worldSpriteMap') or {}
 
   # -------------------------------------------------------------------------
@@ -491,6 +498,11 @@ class WorldModel:
         ip[5] = int(kw.get('canRegrowIfOccupied', True))
         dp[0] = radius
         dp[1:1 + len(probs)] = probs
+        # Layer names are hard-coded in the Lua (commons_harvest/components.lua:149,196-199).
+        ip[6] = self.layers.index('logic')
+        ip[7] = self.layers.index('lowerPhysical')
+        ip[8] = self.layers.index('background')
+        self._needs_grass.append(len(self.comps_i))
       self.comps_i.append([COMP[name]] + ip)
       self.comps_d.append(dp)
     kid = len(self.kinds)
@@ -665,6 +677,93 @@ def _clean_up_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
   sections['cu_dp'] = dp
 
 
+def _commons_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
+  """SoA tables for the commons_harvest step kernel."""
+  W = model.W
+  apples = []
+  for oid, ci in _objects_with(model, 'DensityRegrow'):
+    kid, x, y, orient, st = model.objects[oid]
+    apples.append((oid, y * W + x, st, kid, ci))
+  kid_a, ci_a = apples[0][3], apples[0][4]
+  if any(r[3] != kid_a for r in apples):
+    raise NotImplementedError('heterogeneous apple prefabs')
+  ka = model.kinds[kid_a]
+  dr = model.comps_i[ci_a][1:]
+  drd = model.comps_d[ci_a]
+  live_state, wait0, n_wait, plain_wait, n_probs = dr[0], dr[1], dr[2], dr[3], dr[4]
+  if not dr[5]:
+    raise NotImplementedError('canRegrowIfOccupied=False')
+  live = model.states[ka[0] + live_state]
+  waitk = model.states[ka[0] + wait0]
+  plain = model.states[ka[0] + plain_wait]
+  if plain[0] != waitk[0] or plain[1] != waitk[1]:
+    raise NotImplementedError('wait states with different layers/sprites')
+  edible = [c for c in range(ka[2], ka[2] + ka[3]) if model.comps_i[c][0] == COMP['Edible']][0]
+  if model.comps_i[edible][1] != live_state or model.comps_i[edible][2] != plain_wait:
+    raise NotImplementedError('Edible states differ from DensityRegrow states')
+  # grass under each apple (background layer)
+  grass_kind = [i for i, n in enumerate(model.state_names) if 'grass' in n and 'dessicated' in n][0]
+  gk = model.kinds[grass_kind]
+  gnames = model.state_names[grass_kind]
+  grass_state = model.states[gk[0] + gnames.index('grass')]
+  dess_state = model.states[gk[0] + gnames.index('dessicated')]
+  grass_at = {}
+  for oid, (kid, x, y, orient, st) in enumerate(model.objects):
+    if kid == grass_kind:
+      grass_at[y * W + x] = oid
+  radius = drd[0]
+  cell_to_apple = {r[1]: i for i, r in enumerate(apples)}
+  nbr = np.full((len(apples), 16), -1, np.int32)
+  r_int = int(radius)
+  for i, row in enumerate(apples):
+    cx, cy = row[1] % W, row[1] // W
+    k = 0
+    for dy in range(-r_int, r_int + 1):   # same scan order as the oracle (irrelevant to results)
+      for dx in range(-r_int, r_int + 1):
+        if dx * dx + dy * dy > radius * radius or (dx == 0 and dy == 0):
+          continue
+        x, y = cx + dx, cy + dy
+        if model.topology == 1:
+          x %= W; y %= model.H
+        elif not (0 <= x < W and 0 <= y < model.H):
+          continue
+        j = cell_to_apple.get(y * W + x)
+        if j is not None:
+          nbr[i, k] = j
+          k += 1
+  def avatar_comp(comp):
+    rows = []
+    for oid in model.avatar_objs:
+      k = model.kinds[model.objects[oid][0]]
+      ci = [c for c in range(k[2], k[2] + k[3]) if model.comps_i[c][0] == COMP[comp]][0]
+      rows.append((model.comps_i[ci][1:], model.comps_d[ci]))
+    for r in rows[1:]:
+      if r != rows[0]:
+        raise NotImplementedError(f'per-avatar {comp} parameters')
+    return rows[0]
+  zi, zd = avatar_comp('Zapper')
+  scene_k = model.kinds[model.objects[0][0]]
+  end = [c for c in range(scene_k[2], scene_k[2] + scene_k[3])
+         if model.comps_i[c][0] == COMP['StochasticIntervalEpisodeEnding']][0]
+  ei, ed = model.comps_i[end][1:], model.comps_d[end]
+  hits = {h[0]: (model.layers.index(h[1]), model.sprites.index(h[2])) for h in model.hits}
+  ip = np.zeros(48, np.int32)
+  dp = np.zeros(16, np.float64)
+  ip[0:8] = [len(apples), live[0], live[1], waitk[0], waitk[1], n_wait, n_probs, grass_state[0]]
+  ip[8:10] = [grass_state[1], dess_state[1]]
+  ip[12:18] = [zi[0], zi[1], zi[2], zi[3], zi[4], 0]
+  ip[21:23] = [hits['zapHit'][0], hits['zapHit'][1]]
+  ip[26:28] = [ei[0], ei[1]]
+  dp[0:n_probs] = drd[1:1 + n_probs]
+  dp[4] = model.comps_d[edible][0]
+  dp[5], dp[6] = zd[0], zd[1]
+  dp[7] = ed[0]
+  sections['ch_ip'] = ip
+  sections['ch_dp'] = dp
+  sections['ch_apple'] = np.array([[r[0], r[1], int(r[2] == live_state), grass_at.get(r[1], -1)] for r in apples], np.int32)
+  sections['ch_nbr'] = nbr
+
+
 # ---------------------------------------------------------------------------
 # Entry points
 # ---------------------------------------------------------------------------
@@ -729,6 +828,8 @@ def compile_settings(settings: Mapping[str, Any],
   _avatar_tables(model, sections)
   if model.family == 'clean_up':
     _clean_up_tables(model, sections)
+  elif model.family == 'commons_harvest':
+    _commons_tables(model, sections)
   info = dict(
       level=model.level, family=model.family, layers=model.layers,
       sprites=model.sprites.names, groups=model.groups,

@@ -8,7 +8,7 @@
 //   avatar      i32 [B][P][4]           x, y, orientation, alive
 //   av_timer    i32 [B][P][4]           zap cooldown, second-beam cooldown, frame of last state
 //                                       change, spare
-//   apple/dirt/water u8 [B][n_pad]      per-entity state (family specific)
+//   apple/dirt/water/apple_count u8 [B][n_pad]  per-entity state (family specific)
 //   env         i32 [B][8]              step, episode, done, dirt count, cleaned flags, ate flags,
 //                                       beam-dirty, spare
 // cells_pad keeps every layer row 16-byte aligned so rows can be moved with 128-bit accesses.
@@ -56,6 +56,15 @@ struct Tables {
   BeamGeom clean_geom;
   int dirt_delay, end_min_frames, end_interval, taste_role, dirt_count0;
   double grow_rate, grow_depletion, grow_restoration, eat_reward, dirt_prob, end_prob, taste_amount;
+  // commons_harvest family
+  int wait_layer, wait_sprite, grass_layer, grass_sprite, dess_sprite, ch_n_wait, ch_n_probs;
+  double ch_probs[4];
+  // initial spawn groups (Avatar spawnGroup vs postInitialSpawnGroup, avatar_library.lua:121-125,322-328)
+  int n_spawn_init[2];
+  int avatar_init_group[MP_MAX_PLAYERS];
+  const int32_t* spawn_init_cell[2];
+  const int32_t* ch_apple;     // [nA][4] obj id, cell, initially live, grass obj id
+  const int32_t* ch_nbr;       // [nA][16] apples inside the regrowth disc (excluding self), -1 padded
   // device tables
   const uint16_t* init_grid;   // [L][cells_pad]
   const int32_t* action_table; // [n_actions][4]
@@ -83,12 +92,14 @@ struct State {
   uint8_t* apple;
   uint8_t* dirt;
   uint8_t* water;
+  uint8_t* apple_count;
   int32_t* env;
   // outputs
   double* reward;
   double* discount;
   int64_t* step_type;
   double* scalar_obs;  // [n_scalar][B][P]
+  double* packed;      // [B][P+2] reward..., discount, step type: one buffer for the per-step all-gather
   uint8_t* rgb;
   uint8_t* world_rgb;
 };

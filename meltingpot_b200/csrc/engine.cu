@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "render.cuh"
 #include "step_clean_up.cuh"
+#include "step_commons.cuh"
 
 namespace {
 
@@ -150,62 +151,118 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   if (T.n_actions < 1) return fail(MP_E_INVALID, "blob has no action table (compile with the substrate config)");
   if (T.cells >= 4096) return fail(MP_E_UNSUPPORTED, "map of %d cells (max 4095)", T.cells);
   for (int k = 0; k < T.n_scalar; ++k) T.scalar_obs[k] = scalar_obs.data[k];
-  if (E->family != MPB_FAMILY_CLEAN_UP) return fail(MP_E_UNSUPPORTED, "substrate family %d has no CUDA state-transition kernel yet", E->family);
+  if (E->family != MPB_FAMILY_CLEAN_UP && E->family != MPB_FAMILY_COMMONS_HARVEST) return fail(MP_E_UNSUPPORTED, "substrate family %d has no CUDA state-transition kernel yet", E->family);
 
   // ---- avatars ---------------------------------------------------------------------------------
   T.avatar_layer = av_table.data[2];
-  int spawn_group = av_table.data[3];
+  int init_groups[2] = {-1, -1};
+  int respawn_group = -1;
   for (int p = 0; p < T.P; ++p) {
     const int32_t* a = av_table.data + p * 8;
     T.avatar_sprite[p] = a[1];
-    if (a[2] != T.avatar_layer || a[3] != spawn_group || a[4] != -1) return fail(MP_E_UNSUPPORTED, "per-avatar layers / spawn groups");
+    if (a[2] != T.avatar_layer) return fail(MP_E_UNSUPPORTED, "per-avatar layers");
+    const int post = a[4] >= 0 ? a[4] : a[3];
+    if (respawn_group >= 0 && post != respawn_group) return fail(MP_E_UNSUPPORTED, "per-avatar respawn groups");
+    respawn_group = post;
+    int g = -1;
+    for (int k = 0; k < 2; ++k) if (init_groups[k] == a[3]) g = k;
+    if (g < 0) { for (int k = 0; k < 2 && g < 0; ++k) if (init_groups[k] < 0) { init_groups[k] = a[3]; g = k; } }
+    if (g < 0) return fail(MP_E_UNSUPPORTED, "more than two initial spawn groups");
+    T.avatar_init_group[p] = g;
   }
   char name[64];
-  snprintf(name, sizeof name, "spawn_cells_%d", spawn_group);
-  Section<int32_t> spawn;
-  if (!get_section(blob, n, name, MPB_I32, &spawn)) return fail(MP_E_INVALID, "blob: missing section '%s'", name);
-  T.n_spawn = (int)spawn.count;
-  if (T.n_spawn < T.P || T.n_spawn > 64) return fail(MP_E_UNSUPPORTED, "%d spawn points for %d players (need P..64)", T.n_spawn, T.P);
-
-  // ---- clean_up family tables ------------------------------------------------------------------
-  Section<int32_t> cu_ip, cu_apple, cu_dirt, cu_water, cu_water_sprites;
-  Section<double> cu_dp;
-  NEED(cu_ip, MPB_I32) NEED(cu_dp, MPB_F64) NEED(cu_apple, MPB_I32) NEED(cu_dirt, MPB_I32) NEED(cu_water, MPB_I32) NEED(cu_water_sprites, MPB_I32)
-#undef NEED
-  const int32_t* ip = cu_ip.data; const double* dp = cu_dp.data;
-  T.nA = ip[0]; T.nD = ip[1]; T.nW = ip[2];
-  T.nA_pad = round_up(std::max(T.nA, 1), 16); T.nD_pad = round_up(std::max(T.nD, 1), 16); T.nW_pad = round_up(std::max(T.nW, 1), 16);
-  T.apple_layer = ip[3]; T.apple_sprite = ip[4]; T.dirt_layer = ip[5]; T.dirt_sprite = ip[6];
-  T.water_layer = ip[8]; T.n_anim = ip[9]; T.anim_frames = ip[10]; T.anim_random = ip[11];
-  if (T.n_anim < 1 || T.n_anim > 8 || T.anim_frames < 1) return fail(MP_E_UNSUPPORTED, "animation with %d states / %d frames", T.n_anim, T.anim_frames);
-  for (int i = 0; i < T.n_anim; ++i) T.water_sprite[i] = cu_water_sprites.data[i];
-  T.zap_cooldown = ip[12]; T.zap_respawn = ip[15]; T.zap_remove = ip[16];
-  T.clean_cooldown = ip[18];
-  T.zap_layer = ip[21]; T.zap_sprite = ip[22]; T.clean_layer = ip[23]; T.clean_sprite = ip[24];
-  T.zap_hit = 0; T.clean_hit = 1;
-  for (int h = 0; h < (int)hits.count / 2; ++h) {
-    if (hits.data[h * 2] == T.zap_layer) T.zap_hit = h;
-    if (hits.data[h * 2] == T.clean_layer) T.clean_hit = h;
+  auto load_group = [&](int gid, std::vector<int32_t>* out) -> int {
+    snprintf(name, sizeof name, "spawn_cells_%d", gid);
+    Section<int32_t> sec;
+    if (!get_section(blob, n, name, MPB_I32, &sec)) return fail(MP_E_INVALID, "blob: missing section '%s'", name);
+    out->assign(sec.data, sec.data + sec.count);
+    return MP_OK;
+  };
+  std::vector<int32_t> v_spawn, v_init[2];
+  int rc0;
+  if ((rc0 = load_group(respawn_group, &v_spawn))) return rc0;
+  T.n_spawn = (int)v_spawn.size();
+  for (int k = 0; k < 2; ++k) {
+    T.n_spawn_init[k] = 0;
+    if (init_groups[k] < 0) continue;
+    if ((rc0 = load_group(init_groups[k], &v_init[k]))) return rc0;
+    T.n_spawn_init[k] = (int)v_init[k].size();
+    int users = 0;
+    for (int p = 0; p < T.P; ++p) users += T.avatar_init_group[p] == k;
+    if (T.n_spawn_init[k] < users || T.n_spawn_init[k] > 64) return fail(MP_E_UNSUPPORTED, "%d spawn points for %d avatars (need n..64)", T.n_spawn_init[k], users);
   }
-  if (T.zap_cooldown <= 0 || T.clean_cooldown < 0) return fail(MP_E_UNSUPPORTED, "non-positive beam cooldowns");
-  if (!make_beam_geom(ip[13], ip[14], &T.zap_geom) || !make_beam_geom(ip[19], ip[20], &T.clean_geom))
-    return fail(MP_E_UNSUPPORTED, "beam footprint larger than %d cells", MP_MAX_BEAM_CELLS);
-  T.dirt_delay = ip[25]; T.end_min_frames = ip[26]; T.end_interval = ip[27]; T.taste_role = ip[28];
-  if (T.taste_role != 0) return fail(MP_E_UNSUPPORTED, "Taste roles other than 'free'");
-  if (T.end_interval < 1) return fail(MP_E_INVALID, "episode interval < 1");
-  T.grow_rate = dp[0]; T.grow_depletion = dp[1]; T.grow_restoration = dp[2]; T.eat_reward = dp[3];
-  T.zap_penalty = dp[4]; T.zap_reward = dp[5]; T.dirt_prob = dp[6]; T.end_prob = dp[7]; T.taste_amount = dp[8];
+  if (T.n_spawn < 1) return fail(MP_E_INVALID, "empty respawn group");
+
+  // ---- family tables -----------------------------------------------------------------------------
+  int rc;
+  std::vector<int32_t> v_apple, v_dirt, v_water;
+  T.nA = T.nD = T.nW = 0;
+  T.n_anim = 1; T.anim_frames = 1; T.clean_layer = 0;
+  auto zapper = [&](const int32_t* ip) -> int {  // shared Zapper block of cu_ip / ch_ip
+    T.zap_cooldown = ip[12]; T.zap_respawn = ip[15]; T.zap_remove = ip[16];
+    T.zap_layer = ip[21]; T.zap_sprite = ip[22];
+    T.zap_hit = 0;
+    for (int h = 0; h < (int)hits.count / 2; ++h) if (hits.data[h * 2] == T.zap_layer) T.zap_hit = h;
+    if (T.zap_cooldown <= 0) return fail(MP_E_UNSUPPORTED, "non-positive zap cooldown");
+    if (!make_beam_geom(ip[13], ip[14], &T.zap_geom)) return fail(MP_E_UNSUPPORTED, "beam footprint larger than %d cells", MP_MAX_BEAM_CELLS);
+    T.end_min_frames = ip[26]; T.end_interval = ip[27];
+    if (T.end_interval < 1) return fail(MP_E_INVALID, "episode interval < 1");
+    return MP_OK;
+  };
+  if (E->family == MPB_FAMILY_CLEAN_UP) {
+    Section<int32_t> cu_ip, cu_apple, cu_dirt, cu_water, cu_water_sprites;
+    Section<double> cu_dp;
+    NEED(cu_ip, MPB_I32) NEED(cu_dp, MPB_F64) NEED(cu_apple, MPB_I32) NEED(cu_dirt, MPB_I32) NEED(cu_water, MPB_I32) NEED(cu_water_sprites, MPB_I32)
+    const int32_t* ip = cu_ip.data; const double* dp = cu_dp.data;
+    T.nA = ip[0]; T.nD = ip[1]; T.nW = ip[2];
+    T.apple_layer = ip[3]; T.apple_sprite = ip[4]; T.dirt_layer = ip[5]; T.dirt_sprite = ip[6];
+    T.water_layer = ip[8]; T.n_anim = ip[9]; T.anim_frames = ip[10]; T.anim_random = ip[11];
+    if (T.n_anim < 1 || T.n_anim > 8 || T.anim_frames < 1) return fail(MP_E_UNSUPPORTED, "animation with %d states / %d frames", T.n_anim, T.anim_frames);
+    for (int i = 0; i < T.n_anim; ++i) T.water_sprite[i] = cu_water_sprites.data[i];
+    if ((rc = zapper(ip))) return rc;
+    T.clean_cooldown = ip[18]; T.clean_layer = ip[23]; T.clean_sprite = ip[24];
+    T.clean_hit = 1;
+    for (int h = 0; h < (int)hits.count / 2; ++h) if (hits.data[h * 2] == T.clean_layer) T.clean_hit = h;
+    if (T.clean_cooldown < 0) return fail(MP_E_UNSUPPORTED, "negative clean cooldown");
+    if (!make_beam_geom(ip[19], ip[20], &T.clean_geom)) return fail(MP_E_UNSUPPORTED, "beam footprint larger than %d cells", MP_MAX_BEAM_CELLS);
+    T.dirt_delay = ip[25]; T.taste_role = ip[28];
+    if (T.taste_role != 0) return fail(MP_E_UNSUPPORTED, "Taste roles other than 'free'");
+    T.grow_rate = dp[0]; T.grow_depletion = dp[1]; T.grow_restoration = dp[2]; T.eat_reward = dp[3];
+    T.zap_penalty = dp[4]; T.zap_reward = dp[5]; T.dirt_prob = dp[6]; T.end_prob = dp[7]; T.taste_amount = dp[8];
+    v_apple.assign(cu_apple.data, cu_apple.data + cu_apple.count);
+    v_dirt.assign(cu_dirt.data, cu_dirt.data + cu_dirt.count);
+    v_water.assign(cu_water.data, cu_water.data + cu_water.count);
+    if ((rc = E->upload(v_apple, &T.apple)) || (rc = E->upload(v_dirt, &T.dirt)) || (rc = E->upload(v_water, &T.water))) return rc;
+  } else {  // MPB_FAMILY_COMMONS_HARVEST
+    Section<int32_t> ch_ip, ch_apple, ch_nbr;
+    Section<double> ch_dp;
+    NEED(ch_ip, MPB_I32) NEED(ch_dp, MPB_F64) NEED(ch_apple, MPB_I32) NEED(ch_nbr, MPB_I32)
+    const int32_t* ip = ch_ip.data; const double* dp = ch_dp.data;
+    T.nA = ip[0]; T.apple_layer = ip[1]; T.apple_sprite = ip[2]; T.wait_layer = ip[3]; T.wait_sprite = ip[4];
+    T.ch_n_wait = ip[5]; T.ch_n_probs = ip[6]; T.grass_layer = ip[7]; T.grass_sprite = ip[8]; T.dess_sprite = ip[9];
+    if (T.ch_n_wait < 1 || T.ch_n_wait > 29 || T.ch_n_probs < 1 || T.ch_n_probs > 4) return fail(MP_E_UNSUPPORTED, "DensityRegrow with %d wait states / %d probabilities", T.ch_n_wait, T.ch_n_probs);
+    if (T.nA > 2048) return fail(MP_E_UNSUPPORTED, "%d apples (max 2048)", T.nA);
+    if ((rc = zapper(ip))) return rc;
+    for (int i = 0; i < 4; ++i) T.ch_probs[i] = dp[i];
+    T.eat_reward = dp[4]; T.zap_penalty = dp[5]; T.zap_reward = dp[6]; T.end_prob = dp[7];
+    v_apple.assign(ch_apple.data, ch_apple.data + ch_apple.count);
+    std::vector<int32_t> v_nbr(ch_nbr.data, ch_nbr.data + ch_nbr.count);
+    if ((rc = E->upload(v_apple, &T.ch_apple)) || (rc = E->upload(v_nbr, &T.ch_nbr))) return rc;
+  }
+#undef NEED
+  T.nA_pad = round_up(std::max(T.nA, 1), 16); T.nD_pad = round_up(std::max(std::max(T.nD, T.nA), 1), 16); T.nW_pad = round_up(std::max(T.nW, 1), 16);
 
   // ---- device copies -----------------------------------------------------------------------------
-  int rc;
   std::vector<uint16_t> grid0((size_t)T.L * T.cells_pad, 0);
   for (int l = 0; l < T.L; ++l) memcpy(&grid0[(size_t)l * T.cells_pad], init_grid.data + (size_t)l * T.cells, T.cells * sizeof(uint16_t));
   if ((rc = E->upload(grid0, &T.init_grid))) return rc;
   std::vector<int32_t> act(action_table.data, action_table.data + action_table.count);
   if ((rc = E->upload(act, &T.action_table))) return rc;
-  std::vector<int32_t> v_apple(cu_apple.data, cu_apple.data + cu_apple.count), v_dirt(cu_dirt.data, cu_dirt.data + cu_dirt.count),
-      v_water(cu_water.data, cu_water.data + cu_water.count), v_spawn(spawn.data, spawn.data + spawn.count);
-  if ((rc = E->upload(v_apple, &T.apple)) || (rc = E->upload(v_dirt, &T.dirt)) || (rc = E->upload(v_water, &T.water)) || (rc = E->upload(v_spawn, &T.spawn_cell))) return rc;
+  if ((rc = E->upload(v_spawn, &T.spawn_cell))) return rc;
+  for (int k = 0; k < 2; ++k) {
+    if (v_init[k].empty()) { T.spawn_init_cell[k] = T.spawn_cell; continue; }
+    if ((rc = E->upload(v_init[k], &T.spawn_init_cell[k]))) return rc;
+  }
   std::vector<uint8_t> solid(T.cells_pad, 0), flags(T.cells_pad, 0);
   for (int o = 0; o < m[MPB_META_N_OBJECTS]; ++o) {  // non-avatar pieces that start on the avatar layer
     const int32_t* od = objects.data + o * MPB_OBJ_COLS;
@@ -218,7 +275,8 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   if ((rc = E->upload(solid, &T.solid)) || (rc = E->upload(flags, &T.cell_flags))) return rc;
   std::vector<int16_t> apple_of(T.cells_pad, -1), dirt_of(T.cells_pad, -1);
   T.dirt_count0 = 0;
-  for (int k = 0; k < T.nA; ++k) apple_of[v_apple[k * 3 + 1]] = (int16_t)k;
+  const int apple_cols = E->family == MPB_FAMILY_CLEAN_UP ? 3 : 4;
+  for (int k = 0; k < T.nA; ++k) apple_of[v_apple[k * apple_cols + 1]] = (int16_t)k;
   for (int j = 0; j < T.nD; ++j) { dirt_of[v_dirt[j * 3 + 1]] = (int16_t)j; T.dirt_count0 += v_dirt[j * 3 + 2]; }
   if ((rc = E->upload(apple_of, &T.apple_of_cell)) || (rc = E->upload(dirt_of, &T.dirt_of_cell))) return rc;
 
@@ -375,7 +433,8 @@ int build_plan(mp_engine* E) {
 
 int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int mode, cudaStream_t st) {
   const int blocks = (E->B + 3) / 4;
-  k_step_clean_up<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
+  if (E->family == MPB_FAMILY_CLEAN_UP) k_step_clean_up<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
+  else k_step_commons<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;
@@ -436,7 +495,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   S.B = num_envs; S.seed = seed + env_index_base;
   const size_t B = num_envs, P = T.P;
   if ((rc = E->alloc(B * T.L * T.cells_pad, &S.grid)) || (rc = E->alloc(B * P * 4, &S.avatar)) || (rc = E->alloc(B * P * 4, &S.av_timer)) ||
-      (rc = E->alloc(B * T.nA_pad, &S.apple)) || (rc = E->alloc(B * T.nD_pad, &S.dirt)) || (rc = E->alloc(B * T.nW_pad, &S.water)) ||
+      (rc = E->alloc(B * T.nA_pad, &S.apple)) || (rc = E->alloc(B * T.nD_pad, &S.dirt)) || (rc = E->alloc(B * T.nW_pad, &S.water)) || (rc = E->alloc(B * T.nA_pad, &S.apple_count)) || (rc = E->alloc(B * (P + 2), &S.packed)) ||
       (rc = E->alloc(B * ENV_COLS, &S.env)) || (rc = E->alloc(B * P, &S.reward)) || (rc = E->alloc(B, &S.discount)) ||
       (rc = E->alloc(B, &S.step_type)) || (rc = E->alloc(std::max<size_t>(1, T.n_scalar) * B * P, &S.scalar_obs)) ||
       (rc = E->alloc(B * P * E->R.player_bytes, &S.rgb)) || (rc = E->alloc(B * (size_t)E->R.world_bytes, &S.world_rgb)) ||
@@ -461,12 +520,13 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   }
   cudaError_t ce = cudaFuncSetAttribute(E->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E->R.smem_bytes);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_clean_up, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_commons, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
   if (ce != cudaSuccess) { mp_destroy(E); return fail(MP_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)); }
   mp_buffers& bf = E->buffers;
   bf.num_envs = num_envs; bf.num_players = T.P; bf.rgb_h = E->R.view_h * 8; bf.rgb_w = E->R.view_w * 8;
   bf.world_h = T.H * 8; bf.world_w = T.W * 8; bf.num_actions = T.n_actions; bf.num_scalar_obs = T.n_scalar;
   bf.rgb = S.rgb; bf.world_rgb = S.world_rgb; bf.reward = S.reward; bf.discount = S.discount; bf.step_type = S.step_type;
-  bf.scalar_obs = S.scalar_obs; bf.avatar_state = S.avatar; bf.grid = S.grid;
+  bf.scalar_obs = S.scalar_obs; bf.avatar_state = S.avatar; bf.grid = S.grid; bf.timestep_packed = S.packed;
   bf.grid_layers = T.L; bf.grid_cells = T.cells; bf.grid_cells_padded = T.cells_pad;
   // observations + scalars + actions + one read and one write of the compact grid.
   E->render_bytes = (uint64_t)P * E->R.player_bytes + (uint64_t)E->R.world_bytes + (uint64_t)T.L * T.cells * 2;

@@ -89,6 +89,7 @@ __device__ void clean_up_reset(const Tables& T, const State& S, int b, int lane,
     tm[TM_ZAP] = 0; tm[TM_BEAM2] = 0; tm[TM_FRAME] = 0; tm[3] = 0;
     grid[(size_t)T.avatar_layer * T.cells_pad + cell] = cell_value(T.avatar_sprite[lane], orient);
     S.reward[(size_t)b * T.P + lane] = 0.0;
+    S.packed[(size_t)b * (T.P + 2) + lane] = 0.0;
     for (int k = 0; k < T.n_scalar; ++k)
       S.scalar_obs[((size_t)k * S.B + b) * T.P + lane] = T.scalar_obs[k] == 0 ? 1.0 : 0.0;
   }
@@ -97,6 +98,7 @@ __device__ void clean_up_reset(const Tables& T, const State& S, int b, int lane,
     env[ENV_CLEANED] = 0; env[ENV_ATE] = 0; env[ENV_BEAM] = 0;
     S.discount[b] = 0.0;   // multiplayer_wrapper.py:117 (None -> 0.)
     S.step_type[b] = 0;    // dm_env.StepType.FIRST
+    S.packed[(size_t)b * (T.P + 2) + T.P] = 0.0; S.packed[(size_t)b * (T.P + 2) + T.P + 1] = 0.0;
   }
   __syncwarp();
 }
@@ -410,6 +412,7 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
     *reinterpret_cast<int4*>(S.avatar + ((size_t)b * T.P + lane) * 4) = make_int4(x, y, orient, alive);
     *reinterpret_cast<int4*>(S.av_timer + ((size_t)b * T.P + lane) * 4) = make_int4(zap_cool, clean_cool, state_frame, 0);
     S.reward[(size_t)b * T.P + lane] = reward;
+    S.packed[(size_t)b * (T.P + 2) + lane] = reward;
     for (int k = 0; k < T.n_scalar; ++k) {
       double v;
       if (T.scalar_obs[k] == 0)  // Zapper:readyToShoot (avatar_library.lua:737-744)
@@ -424,6 +427,8 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
     env[ENV_CLEANED] = (int)cleaned_now; env[ENV_ATE] = (int)ate_now; env[ENV_BEAM] = beam_dirty;
     S.discount[b] = done ? 0.0 : 1.0;
     S.step_type[b] = done ? 2 : 1;
+    S.packed[(size_t)b * (T.P + 2) + T.P] = done ? 0.0 : 1.0;
+    S.packed[(size_t)b * (T.P + 2) + T.P + 1] = done ? 2.0 : 1.0;
   }
 }
 

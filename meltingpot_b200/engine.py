@@ -40,6 +40,7 @@ class MpBuffers(ctypes.Structure):
       ('avatar_state', ctypes.c_void_p), ('grid', ctypes.c_void_p),
       ('grid_layers', ctypes.c_int32), ('grid_cells', ctypes.c_int32),
       ('grid_cells_padded', ctypes.c_int32),
+      ('timestep_packed', ctypes.c_void_p),
   ]
 
 
@@ -151,6 +152,7 @@ class Engine:
     self.scalar_obs = view(bufs.scalar_obs, (max(self.num_scalar_obs, 1), B, P), '<f8', torch.float64)
     self.avatar_state = view(bufs.avatar_state, (B, P, 4), '<i4', torch.int32)
     self.grid = view(bufs.grid, (B, bufs.grid_layers, bufs.grid_cells_padded), '<i2', torch.int16)
+    self.timestep_packed = view(bufs.timestep_packed, (B, P + 2), '<f8', torch.float64)
 
   # -- lifecycle -----------------------------------------------------------------
   def close(self) -> None:

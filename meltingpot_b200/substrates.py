@@ -10,6 +10,7 @@ _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
 # substrate -> player counts with a committed blob (default roles repeated).
 PRECOMPILED = {
     'clean_up': (7,),
+    'commons_harvest__open': (7, 16),
 }
 
 

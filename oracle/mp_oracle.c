@@ -76,6 +76,7 @@ typedef struct {
   int clean_cool, player_cleaned;                    /* Cleaner */
   int player_ate;                                    /* Taste */
   int num_others_cleaned, num_others_ate;            /* AllNonselfCumulants */
+  int num_neighbors, dr_started, grass_obj;          /* DensityRegrow */
 } Obj;
 
 enum { ACT_SET_STATE, ACT_TURN, ACT_MOVE_REL, ACT_TELEPORT_GROUP, ACT_BEAM };
@@ -86,7 +87,7 @@ typedef struct { int type, a, b; } Event;
 
 enum { /* updater function ids */
   UF_AVATAR_MOVE, UF_ZAP, UF_RESPAWN, UF_CLEAN, UF_CLEANER_RESET, UF_TASTE_RESET, UF_NONSELF_GET,
-  UF_NONSELF_RESET, UF_GLOBAL_RESET, UF_EPISODE_END, UF_ANIMATION
+  UF_NONSELF_RESET, UF_GLOBAL_RESET, UF_EPISODE_END, UF_ANIMATION, UF_SPROUT
 };
 typedef struct { int priority, comp_type, fn, seq; } Updater;
 
@@ -127,6 +128,7 @@ static const CompDef* find_comp(const OrEnv* e, const Obj* o, int type) {
   return 0;
 }
 static inline int cell_of(const OrEnv* e, int x, int y) { return y * e->W + x; }
+static int wrap_or_reject(const OrEnv* e, int* x, int* y);
 
 static void enqueue(OrEnv* e, int type, int obj, int a, int b, int c) {
   if (e->qnn == e->qncap) { e->qncap = e->qncap ? e->qncap * 2 : 256; e->qnext = (Action*)realloc(e->qnext, sizeof(Action) * e->qncap); }
@@ -220,6 +222,39 @@ static int on_hit(OrEnv* e, int target, int shooter, int hit) {
   return blocked;
 }
 
+/* DensityRegrow:_getNeighbors (commons_harvest/components.lua:195-204): pieces on the wait layer
+ * ('logic') and on the live layer ('lowerPhysical') inside the disc transform:queryDisc(layer, radius). */
+static int in_disc(double radius, int dx, int dy) { return (double)(dx * dx + dy * dy) <= radius * radius; }
+static void density_begin_live(OrEnv* e, int oi, const CompDef* c) { /* :206-219 */
+  Obj* o = &e->obj[oi];
+  int cells = e->W * e->H, r = (int)c->dp[0];
+  for (int dy = -r; dy <= r; ++dy) for (int dx = -r; dx <= r; ++dx) {
+    if (!in_disc(c->dp[0], dx, dy)) continue;
+    int x = o->x + dx, y = o->y + dy;
+    if (!wrap_or_reject(e, &x, &y)) continue;
+    int q = e->grid[c->ip[6] * cells + cell_of(e, x, y)] - 1;
+    if (q >= 0 && q != oi) e->obj[q].num_neighbors += 1;
+  }
+}
+static void density_end_live(OrEnv* e, int oi, const CompDef* c) { /* :221-240 */
+  Obj* o = &e->obj[oi];
+  int cells = e->W * e->H, r = (int)c->dp[0], live = 0;
+  for (int dy = -r; dy <= r; ++dy) for (int dx = -r; dx <= r; ++dx) {
+    if (!in_disc(c->dp[0], dx, dy)) continue;
+    int x = o->x + dx, y = o->y + dy;
+    if (!wrap_or_reject(e, &x, &y)) continue;
+    if (e->grid[c->ip[7] * cells + cell_of(e, x, y)]) ++live;
+  }
+  for (int dy = -r; dy <= r; ++dy) for (int dx = -r; dx <= r; ++dx) {
+    if (!in_disc(c->dp[0], dx, dy)) continue;
+    int x = o->x + dx, y = o->y + dy;
+    if (!wrap_or_reject(e, &x, &y)) continue;
+    int q = e->grid[c->ip[6] * cells + cell_of(e, x, y)] - 1;
+    if (q < 0) continue;
+    if (q != oi) e->obj[q].num_neighbors -= 1; else e->obj[q].num_neighbors = live;
+  }
+}
+
 /* GameObject:_onAdd -> component onStateChange(previousState) (game_object.lua:273-285). */
 static void on_state_change(OrEnv* e, int oi, int old_state) {
   Obj* o = &e->obj[oi];
@@ -233,6 +268,12 @@ static void on_state_change(OrEnv* e, int oi, int old_state) {
         break;
       case MPB_C_AVATAR: /* avatar_library.lua:430-453 */
         if (old_state == c->ip[2] && o->state == c->ip[1]) { o->freeze = 0; o->removal = 0; }
+        break;
+      case MPB_C_DENSITY_REGROW: /* commons_harvest/components.lua:153-163 */
+        if (o->dr_started) {
+          if (o->state == c->ip[0]) density_begin_live(e, oi, c);
+          else if (old_state == c->ip[0]) density_end_live(e, oi, c);
+        }
         break;
       default: break;
     }
@@ -426,6 +467,13 @@ static void run_updater(OrEnv* e, const Updater* u, int oi) {
         if (u01(w[0], w[1]) < c->dp[0]) e->cont = 0; /* simulation:endEpisode() */
       }
     } break;
+    case UF_SPROUT: { /* commons_harvest/components.lua:92-123: one updater per wait_k state, priority 10 */
+      int k = o->state - c->ip[1];
+      if (k < 0 || k >= c->ip[2]) break;
+      int idx = k < c->ip[4] ? k : c->ip[4] - 1;
+      uint32_t w[4]; rng(e, RS_OBJECT, oi, w);
+      if (u01(w[0], w[1]) < c->dp[1 + idx]) enqueue(e, ACT_SET_STATE, oi, c->ip[0], 0, 0); /* canRegrowIfOccupied */
+    } break;
     case UF_ANIMATION: { /* component_library.lua:1070-1094: one updater per state, startFrame */
       if (age < c->ip[9]) break;
       int n = c->ip[0];
@@ -462,6 +510,7 @@ static void build_updaters(OrEnv* e) {
         case MPB_C_GLOBAL_DATA: add_updater(e, 2, MPB_C_GLOBAL_DATA, UF_GLOBAL_RESET); break;
         case MPB_C_STOCHASTIC_INTERVAL_EPISODE_ENDING: add_updater(e, 100, MPB_C_STOCHASTIC_INTERVAL_EPISODE_ENDING, UF_EPISODE_END); break;
         case MPB_C_ANIMATION: add_updater(e, 100, MPB_C_ANIMATION, UF_ANIMATION); break;
+        case MPB_C_DENSITY_REGROW: add_updater(e, 10, MPB_C_DENSITY_REGROW, UF_SPROUT); break;
         default: break;
       }
     }
@@ -528,6 +577,13 @@ static void simulation_update(OrEnv* e) {
           o->freeze = o->freeze > 0 ? o->freeze - 1 : 0;
           if (o->removal == 1) enqueue(e, ACT_SET_STATE, oi, c->ip[2], 0, 0);
           o->removal = o->removal > 0 ? o->removal - 1 : 0;
+        } break;
+        case MPB_C_DENSITY_REGROW: { /* DensityRegrow:update -> _updateWaitState (commons_harvest/components.lua:147-151,170-193) */
+          if (o->layer != c->ip[6] || o->state == c->ip[0]) break;
+          int kk = o->num_neighbors;
+          if (kk >= c->ip[2]) kk = c->ip[2] - 1;
+          enqueue(e, ACT_SET_STATE, oi, c->ip[1] + kk, 0, 0);
+          if (o->grass_obj >= 0) enqueue(e, ACT_SET_STATE, o->grass_obj, kk == 0 ? c->ip[10] : c->ip[9], 0, 0);
         } break;
         case MPB_C_APPLE_GROW: { /* clean_up/components.lua:64-80 */
           double dirt = (double)e->dirt_count, clean = (double)e->clean_count;
@@ -598,6 +654,11 @@ static void episode_start(OrEnv* e) {
       if (c->type == MPB_C_ANIMATION && c->ip[11]) { /* component_library.lua:1064-1068 */
         uint32_t w[4]; rng(e, RS_OBJECT_RESET, oi, w);
         enqueue(e, ACT_SET_STATE, oi, c->ip[1 + pick(w[0], (uint32_t)c->ip[0])], 0, 0);
+      } else if (c->type == MPB_C_DENSITY_REGROW) { /* start :139-145, postStart :147-152 */
+        o->num_neighbors = 0;
+        density_begin_live(e, oi, c);
+        o->dr_started = 1;
+        o->grass_obj = e->grid[c->ip[8] * (e->W * e->H) + cell_of(e, o->x, o->y)] - 1;
       } else if (c->type == MPB_C_DIRT_TRACKER) {    /* clean_up/components.lua:103-116 */
         if (o->state == c->ip[1]) e->clean_count++; else if (o->state == c->ip[0]) e->dirt_count++;
       }

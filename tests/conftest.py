@@ -29,3 +29,15 @@ def oracle():
 def clean_river_blob():
   with open(os.path.join(ROOT, 'tests', 'golden', 'clean_up_clean_river__7p.mpb'), 'rb') as f:
     return f.read()
+
+
+@pytest.fixture(scope='session')
+def commons_blob():
+  from meltingpot_b200 import substrates
+  return substrates.load_blob('commons_harvest__open', ('default',) * 7)
+
+
+@pytest.fixture(scope='session')
+def commons16_blob():
+  from meltingpot_b200 import substrates
+  return substrates.load_blob('commons_harvest__open', ('default',) * 16)

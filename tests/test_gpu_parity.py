@@ -113,3 +113,14 @@ def ts_first_world(seed):
   from meltingpot_b200 import substrate
   with substrate.build('clean_up', roles=('default',) * 7, env_seed=seed) as env:
     return env.reset().observation[0]['WORLD.RGB']
+
+
+def test_commons_harvest_random_rollout(commons_blob, oracle):
+  stats = parity.compare_rollout(commons_blob, oracle, num_envs=16, steps=500, seed=3, pixels_every=3)
+  assert stats['eaten'] > 50 and stats['zaps'] > 0
+
+
+def test_commons_harvest_16_players(commons16_blob, oracle):
+  # BASELINE.json config 3 shape: 16 players (2 inside spawn points + 60 outside).
+  stats = parity.compare_rollout(commons16_blob, oracle, num_envs=8, steps=400, seed=11, pixels_every=5)
+  assert stats['eaten'] > 50
