@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
           self.samples.append([s.strip() for s in out.split(',')])
       except Exception:  # pylint: disable=broad-except
         pass
-      self._halt.wait(0.1)
+      self._halt.wait(0.05)
 
   def stop(self):
     self._halt.set()
@@ -161,17 +161,23 @@ def run_b200(args, rank, world, local_rank):
   actions = torch.randint(0, A, (K + Wm, B, P), generator=gen, device=dev, dtype=torch.int32)
   stream = torch.cuda.current_stream(dev)
   gathered = None
+  side = None
   if world > 1:
-    scal = torch.empty((B, P + 2), dtype=torch.float64, device=dev)
     gathered = torch.empty((world * B, P + 2), dtype=torch.float64, device=dev)
+    side = torch.cuda.Stream(device=dev)
 
   def one_step(t):
-    eng.step(actions[t])
-    if world > 1:  # stack the scalar timestep fields of all shards on every rank
-      scal[:, :P] = eng.reward
-      scal[:, P] = eng.discount
-      scal[:, P + 1] = eng.step_type.to(torch.float64)
-      dist.all_gather_into_tensor(gathered, scal)
+    if world == 1:
+      eng.step(actions[t])
+      return
+    # The scalar timestep (reward, discount, step type: one packed f64 buffer written by the step
+    # kernel) is all-gathered on a side stream while the render kernel runs on the main stream.
+    stream.wait_stream(side)            # last step's gather has finished reading timestep_packed
+    eng.step_state(actions[t])
+    side.wait_stream(stream)
+    with torch.cuda.stream(side):
+      dist.all_gather_into_tensor(gathered, eng.timestep_packed)
+    eng.render()
 
   eng.reset()
   for t in range(Wm):
@@ -188,6 +194,8 @@ def run_b200(args, rank, world, local_rank):
   ev0.record(stream)
   for t in range(Wm, Wm + K):
     one_step(t)
+  if side is not None:
+    stream.wait_stream(side)
   ev1.record(stream)
   torch.cuda.synchronize()
   if world > 1:
@@ -245,7 +253,7 @@ def run_b200(args, rank, world, local_rank):
                         'WORLD.RGB on (BASELINE.json configs[1])',
             'envs_per_gpu': B, 'players': P, 'global_envs': world * B,
             'cache': 'per-step working set 1.2 GB of freshly written observations >> 126 MB L2; no explicit flush',
-            'multi_gpu': 'env shards, no data-path collective; per-step NCCL all-gather of reward/discount/step_type' if world > 1 else 'single GPU',
+            'multi_gpu': 'env shards, no data-path collective; per-step NCCL all-gather of the packed reward/discount/step_type buffer on a side stream, overlapped with rendering' if world > 1 else 'single GPU',
         },
         'agent_steps_per_sec': value * P,
         'gpu_launches': launches,
@@ -269,8 +277,8 @@ def run_b200(args, rank, world, local_rank):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=200)
-  ap.add_argument('--warmup', type=int, default=10)
+  ap.add_argument('--steps', type=int, default=2000)
+  ap.add_argument('--warmup', type=int, default=20)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--envs', type=int, default=4096, help='env instances per GPU')
   ap.add_argument('--e2e-steps', type=int, default=30)

@@ -410,7 +410,8 @@ int build_plan(mp_engine* E) {
   R.view_w = T.view_l + T.view_r + 1; R.view_h = T.view_f + T.view_b + 1;
   R.player_bytes = R.view_w * R.view_h * 192;
   R.world_bytes = T.H * T.W * 192;
-  R.stage_bytes = 2 * round_up(std::max(R.view_w * 192, T.W * 48), 128);
+  R.wstrip_log2 = 2;  // 4 pixel rows per WORLD.RGB strip
+  R.stage_bytes = 2 * round_up(std::max(R.view_w * 192, T.W * 24 * (1 << R.wstrip_log2)), 128);
   R.grid_bytes = T.L * T.cells_pad * 2;
   R.n_total = E->n_total;
   R.atlas_bytes = R.n_total * 1024;
@@ -511,12 +512,12 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
     if (ce != cudaSuccess) { mp_destroy(E); return fail(MP_E_CUDA, "cudaMemcpy(env) failed: %s", cudaGetErrorString(ce)); }
   }
   E->step_smem = warp_scratch_bytes(T);
-  {  // cells per lane per strip: ceil(view_w / 4) for player rows, ceil(W / 16) for world quarter-rows
-    const int ncp = (E->R.view_w + 3) / 4, ncw = (T.W + 15) / 16;
-    if (ncp <= 3 && ncw <= 2) E->render_fn = k_render<3, 2>;
-    else if (ncp <= 4 && ncw <= 2) E->render_fn = k_render<4, 2>;
+  {  // cells per lane per strip: ceil(view_w / 4) for player rows, ceil(W / 8) for world half-rows
+    const int ncp = (E->R.view_w + 3) / 4, ncw = (T.W + (32 >> E->R.wstrip_log2) - 1) / (32 >> E->R.wstrip_log2);
+    if (ncp <= 3 && ncw <= 3) E->render_fn = k_render<3, 3>;
+    else if (ncp <= 3 && ncw <= 4) E->render_fn = k_render<3, 4>;
     else if (ncp <= 4 && ncw <= 4) E->render_fn = k_render<4, 4>;
-    else { mp_destroy(E); return fail(MP_E_UNSUPPORTED, "view of %d cells / map of %d cells wide (max 16 / 64)", E->R.view_w, T.W); }
+    else { mp_destroy(E); return fail(MP_E_UNSUPPORTED, "view of %d cells / map of %d cells wide (max 16 / 32)", E->R.view_w, T.W); }
   }
   cudaError_t ce = cudaFuncSetAttribute(E->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E->R.smem_bytes);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_clean_up, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));

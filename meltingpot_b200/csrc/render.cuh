@@ -40,6 +40,7 @@ struct RenderPlan {  // host-computed constants of the tiling
   // shared memory offsets
   int off_atlas, off_pair, off_map, off_team0, team_stride;
   int toff_grid, toff_rec, toff_stage;  // within a team's region
+  int wstrip_log2;                      // log2 of the pixel rows per WORLD.RGB strip (1 or 2)
   int stage_bytes;                      // warp-private staging buffer: two slots, each one player cell-row or half a world cell-row
   int smem_bytes;
 };
@@ -151,7 +152,7 @@ struct ViewerInfo {  // per player, refreshed once per env
 
 // Work decomposition: an env is rendered by one team; after the per-cell pass its warps pull
 // strip items from a shared counter -- one row of view cells (8 pixel rows) of a player image, or
-// a quarter cell row (2 pixel rows) of WORLD.RGB -- compose them into a warp-private staging slot and
+// a half / quarter cell row (4 / 2 pixel rows) of WORLD.RGB -- compose them into a warp-private staging slot and
 // hand the slot to the TMA store engine. Three team barriers per env; everything else is warp-local.
 // Each lane handles NC cells per strip with the loads of all NC cells issued before any is packed.
 template <int NCP, int NCW>
@@ -199,9 +200,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
   if (first >= S.B) return;
 
   const int n_player_items = (flags & 2u) ? T.P * R.view_h : 0;
-  const int n_items = n_player_items + ((flags & 1u) ? 4 * T.H : 0);
+  const int wlog = R.wstrip_log2, wrows = 1 << wlog;  // pixel rows per WORLD.RGB strip (2 or 4)
+  const int n_items = n_player_items + ((flags & 1u) ? (8 >> wlog) * T.H : 0);
   const int prow_bytes = R.view_w * 24, wrow_bytes = T.W * 24;
-  const int pitem_bytes = prow_bytes * 8, witem_bytes = wrow_bytes * 2;
+  const int pitem_bytes = prow_bytes * 8, witem_bytes = wrow_bytes * wrows;
   const int slot_bytes = R.stage_bytes >> 1;
   const int h_oob = REC_FAST | (T.oob_sprite * 4), h_oov = REC_FAST | (T.oov_sprite * 4);
   uint32_t slot = 0;
@@ -297,8 +299,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
         __syncwarp();
         if (lane == 0) bulk_store(S.rgb + ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * pitem_bytes, buf, (uint32_t)pitem_bytes);
       } else {
-        const int wi = item - n_player_items, wy = wi >> 2;
-        const int py = ((wi & 3) << 1) | (lane & 1), cg = lane >> 1;
+        const int wi = item - n_player_items, wy = wi >> (3 - wlog);
+        const int py = ((wi & ((8 >> wlog) - 1)) << wlog) | (lane & (wrows - 1)), cg = lane >> wlog;
+        const int cstep = 32 >> wlog;
         const int16_t* map = s_map + T.P * R.n_total;
         const uint16_t* rowrec = s_rec + wy * T.W * R.rec_stride;
         int hdr[NCW];
@@ -306,12 +309,12 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
         if (!(flags & 16u)) {
 #pragma unroll
         for (int i = 0; i < NCW; ++i) {
-          const int cx = min(cg + 16 * i, T.W - 1);
+          const int cx = min(cg + cstep * i, T.W - 1);
           hdr[i] = rowrec[cx * R.rec_stride];
         }
 #pragma unroll
         for (int i = 0; i < NCW; ++i) {
-          const int cx = min(cg + 16 * i, T.W - 1);
+          const int cx = min(cg + cstep * i, T.W - 1);
           if (hdr[i] & REC_FAST) fast_row(px[i], s_atlas, hdr[i], 0, py);
           else {
 #pragma unroll
@@ -321,8 +324,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
         }
 #pragma unroll
         for (int i = 0; i < NCW; ++i) {
-          const int cx = cg + 16 * i;
-          if (cx < T.W) store_row(buf + (py & 1) * wrow_bytes + cx * 24, px[i]);
+          const int cx = cg + cstep * i;
+          if (cx < T.W) store_row(buf + (py & (wrows - 1)) * wrow_bytes + cx * 24, px[i]);
         }
         }
         fence_async_smem();
