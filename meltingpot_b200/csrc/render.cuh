@@ -70,9 +70,22 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// TMA bulk copy shared -> global.
-__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+// TMA bulk copy shared -> global. Observations are written once and not read again by the engine,
+// so they are tagged evict-first: the 47 MB of env state stays L2-resident instead.
+__device__ __forceinline__ uint64_t make_evict_first_policy() {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t policy) {
+#ifdef MP_NO_STORE_HINT
+  (void)policy;
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+#else
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes), "l"(policy)
+               : "memory");
+#endif
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 template <int N>
@@ -206,6 +219,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
   const int pitem_bytes = prow_bytes * 8, witem_bytes = wrow_bytes * wrows;
   const int slot_bytes = R.stage_bytes >> 1;
   const int h_oob = REC_FAST | (T.oob_sprite * 4), h_oov = REC_FAST | (T.oov_sprite * 4);
+  const uint64_t store_policy = make_evict_first_policy();
   uint32_t slot = 0;
   int it = 0;
   for (int b = first; b < S.B; b += n_streams, ++it) {
@@ -297,7 +311,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
         }
         fence_async_smem();  // make this lane's writes visible to the async (TMA) proxy
         __syncwarp();
-        if (lane == 0) bulk_store(S.rgb + ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * pitem_bytes, buf, (uint32_t)pitem_bytes);
+        if (lane == 0) bulk_store(S.rgb + ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * pitem_bytes, buf, (uint32_t)pitem_bytes, store_policy);
       } else {
         const int wi = item - n_player_items, wy = wi >> (3 - wlog);
         const int py = ((wi & ((8 >> wlog) - 1)) << wlog) | (lane & (wrows - 1)), cg = lane >> wlog;
@@ -330,7 +344,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wi * witem_bytes, buf, (uint32_t)witem_bytes);
+        if (lane == 0) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wi * witem_bytes, buf, (uint32_t)witem_bytes, store_policy);
       }
     }
     team_sync(team);  // every warp is done with s_rec / s_view
