@@ -22,7 +22,7 @@ extern "C" {
 #endif
 
 #define MPB_MAGIC "MPB1"
-#define MPB_VERSION 3u
+#define MPB_VERSION 4u
 #define MPB_NAME_LEN 32
 
 enum MpbDtype { MPB_U8 = 0, MPB_U16 = 1, MPB_I32 = 2, MPB_F64 = 3, MPB_I64 = 4, MPB_CHAR = 5 };
@@ -109,10 +109,22 @@ enum MpbComp {
   MPB_C_DENSITY_REGROW = 23,   /* ip0 live state, ip1 first wait_k state, ip2 n wait_k states, ip3 plain wait state,
                                   ip4 n probabilities, ip5 canRegrowIfOccupied; dp0 radius, dp1.. probabilities */
   MPB_C_LOCATION_OBSERVER = 24,
+  MPB_C_ALL_BEAM_BLOCKER = 25,
+  MPB_C_RESOURCE = 26,         /* ip0 initialHealth, ip1 destroyed state, ip2 rewardDelay, ip3 delayTillSelfRepair, ip4 claimed_by_1 state,
+                                  ip5 initial state, ip6 claimedResources group, ip7 texture layer, ip8 damage-indicator layer,
+                                  ip9 texture 'destroyed' state, ip10 damage 'inactive' state, ip11 damage 'damaged' state;
+                                  dp0 reward, dp1 rewardRate, dp2 selfRepairProbability */
+  MPB_C_RESOURCE_CLAIMER = 27, /* ip0 player index0, ip1 beamLength, ip2 beamRadius, ip3 beamWait, ip4 claimBeam hit id */
+  MPB_C_REWARD_INDICATOR = 28, /* ip0 'inactive' state, ip1 dry_claimed_by_1 state, ip2 resource layer */
+  MPB_C_PAINTBRUSH = 29,       /* ip0 player index0, ip1 directionHit id */
+  MPB_C_GRADUATED_SANCTIONS_MARKING = 30, /* ip0 player index0, ip1 wait state, ip2 initialLevel, ip3 recoveryTime|-1, ip4 hit id,
+                                  ip5 n levels, ip6 level_1 state, ip(7+3l) levelIncrement, ip(8+3l) remove, ip(9+3l) freeze;
+                                  dp(2l) sourceReward, dp(2l+1) targetReward */
+  MPB_C_TERRITORY_TASTE = 31,  /* ip0 role (0 none, 1 rewarded_per_claim, 2 rewarded_per_claim_only); dp0 rewardAmount, dp1 firstClaimRewardMultiplier */
   MPB_C_COUNT
 };
 
-#define MPB_COMP_NI 12
+#define MPB_COMP_NI 16
 #define MPB_COMP_ND 6
 
 /* Columns of int32 tables. */

@@ -8,7 +8,7 @@ from typing import Dict, Mapping
 import numpy as np
 
 MAGIC = b'MPB1'
-VERSION = 3
+VERSION = 4
 NAME_LEN = 32
 
 _DTYPES = {

@@ -47,8 +47,10 @@ COMP = dict(StateManager=1, Transform=2, Appearance=3, BeamBlocker=4, Edible=5,
             AllNonselfCumulants=14, AvatarMetricReporter=15, RiverMonitor=16,
             DirtSpawner=17, StochasticIntervalEpisodeEnding=18, GlobalData=19,
             Animation=20, AdditionalSprites=21, Neighborhoods=22,
-            DensityRegrow=23, LocationObserver=24)
-COMP_NI, COMP_ND = 12, 6
+            DensityRegrow=23, LocationObserver=24, AllBeamBlocker=25,
+            Resource=26, ResourceClaimer=27, RewardIndicator=28, Paintbrush=29,
+            GraduatedSanctionsMarking=30, TerritoryTaste=31)
+COMP_NI, COMP_ND = 16, 6
 ACTION_FIELDS = {'move': 0, 'turn': 1, 'fireZap': 2, 'fireClean': 3,
                  'fireClaim': 3}
 SCALAR_OBS = {'READY_TO_SHOOT': 0, 'NUM_OTHERS_WHO_CLEANED_THIS_STEP': 1}
@@ -56,6 +58,7 @@ COMPASS = {'N': 0, 'E': 1, 'S': 2, 'W': 3}
 BASE_LAYERS = ['logic', 'alternateLogic', 'background', 'lowerPhysical',
                'upperPhysical', 'overlay', 'superOverlay']
 _TASTE_ROLES = {'free': 0, 'cleaner': 1, 'consumer': 2}
+_TERRITORY_TASTE_ROLES = {'none': 0, 'rewarded_per_claim': 1, 'rewarded_per_claim_only': 2}
 _HIT_OF = {'Zapper': ('zapHit', 'beamZap', 'BeamZap'),
            'Cleaner': ('cleanHit', 'beamClean', 'BeamClean')}
 
@@ -124,7 +127,9 @@ def _rgba(color: Sequence[int]) -> List[int]:
 
 def text_to_image(text: str, palette: Mapping[str, Sequence[int]]) -> np.ndarray:
   """ASCII shape + palette -> uint8 [h, w, 4] (component_library.lua:567-597)."""
-  rows = [r for r in text.strip('\n').split('\n')]
+  # Lines are trimmed: territory.py:512-521 indents its sprite text.
+  rows = [r.strip() for r in text.strip().split('\n')]
+  rows = [r for r in rows if r]
   h, w = len(rows), len(rows[0])
   img = np.zeros((h, w, 4), np.uint8)
   for y, row in enumerate(rows):
@@ -292,18 +297,28 @@ class WorldModel:
 
     # ---- layers, hits (base_simulation.lua:263-271; addHits) ---------------
     self.layers = list(BASE_LAYERS)
-    if self.family == 'territory':
-      # lua/levels/territory/init.lua:30-37 appends two render layers.
-      self.layers += ['directionIndicatorLayer', 'superDirectionIndicatorLayer']
     self.hits: List[tuple] = []  # (name, layer, sprite)
+    def add_hit(hit, layer, sprite, insert_layer):
+      if hit not in [h[0] for h in self.hits]:
+        self.hits.append((hit, layer, sprite))
+      if insert_layer and layer not in self.layers:
+        self.layers.append(layer)
     for cfg, _, _ in objs:
       for c in cfg['components']:
+        kw = c.get('kwargs', {}) or {}
         if c['component'] in _HIT_OF:
           hit, layer, sprite = _HIT_OF[c['component']]
-          if hit not in [h[0] for h in self.hits]:
-            self.hits.append((hit, layer, sprite))
-          if layer not in self.layers:
-            self.layers.append(layer)
+          add_hit(hit, layer, sprite, True)
+        elif c['component'] == 'ResourceClaimer':  # territory/components.lua:241-246
+          i = int(kw['playerIndex'])
+          add_hit(f'claimBeam_{i}', 'superDirectionIndicatorLayer', f'claimBeamSprite_{i}', False)
+        elif c['component'] == 'Paintbrush':       # territory/components.lua:387-396
+          i = int(kw['playerIndex'])
+          add_hit(f'directionHit{i}', 'directionIndicatorLayer', f'brush{i}', False)
+    if self.family == 'territory':
+      # lua/levels/territory/init.lua:30-37 appends two render layers after BaseSimulation's own
+      # (which by then include the hit layers added by Zapper:addHits).
+      self.layers += ['directionIndicatorLayer', 'superDirectionIndicatorLayer']
 
     # ---- sprites (base_simulation.lua:322-329) -----------------------------
     sp = SpriteSet(self.sprite_size)
@@ -320,6 +335,10 @@ class WorldModel:
           sp.add_color('BeamZap', kw.get('beamColor', (252, 252, 106)))
         elif c['component'] == 'Cleaner':
           sp.add_color('BeamClean', (99, 223, 242, 175))
+        elif c['component'] == 'ResourceClaimer':
+          sp.add_color(f"claimBeamSprite_{int(kw['playerIndex'])}", kw['color'])
+        elif c['component'] == 'Paintbrush':  # four explicit facings, noRotate (components.lua:374-385)
+          sp.add_shape(f"brush{int(kw['playerIndex'])}", list(kw['shape']), kw['palette'], True)
     self.sprites = sp
 
     # ---- groups -------------------------------------------------------------
@@ -369,6 +388,17 @@ class WorldModel:
         self.avatar_objs.append(oid)
     if len(self.avatar_objs) != self.num_players:
       raise ValueError('number of avatar objects != numPlayers')
+    for ci, comp in enumerate(self.comps_i):
+      if comp[0] == COMP['Resource']:  # territory/components.lua:177-182 (queryPosition layers are hard-coded)
+        tex = self.state_names[self.kind_names.index('resource_texture')]
+        dmg = self.state_names[self.kind_names.index('damage_indicator')]
+        comp[1 + 7] = self.layers.index('lowerPhysical')
+        comp[1 + 8] = self.layers.index('superDirectionIndicatorLayer')
+        comp[1 + 9] = tex.index('destroyed')
+        comp[1 + 10] = dmg.index('inactive')
+        comp[1 + 11] = dmg.index('damaged')
+      elif comp[0] == COMP['RewardIndicator']:  # :293-300
+        comp[1 + 2] = self.layers.index('upperPhysical')
     for ci in self._needs_grass:  # DensityRegrow toggles the underlying grass (components.lua:181-193)
       grass = [n for n in self.state_names if 'grass' in n and 'dessicated' in n]
       if not grass:
@@ -464,7 +494,7 @@ class WorldModel:
       elif name == 'Cleaner':
         ip[0], ip[1], ip[2] = int(kw['cooldownTime']), int(kw['beamLength']), int(kw['beamRadius'])
         ip[3] = hit_id('cleanHit')
-      elif name == 'Taste':
+      elif name == 'Taste' and self.family != 'territory':
         ip[0] = _TASTE_ROLES[kw.get('role', 'free')]
         dp[0] = float(kw.get('rewardAmount', 1))
       elif name == 'DirtSpawner':
@@ -484,6 +514,50 @@ class WorldModel:
         ip[9] = int(kw['gameFramesPerAnimationFrame'])
         ip[10] = int(kw['loop'])
         ip[11] = int(kw.get('randomStartFrame', False))
+      elif name == 'Taste' and self.family == 'territory':
+        name = 'TerritoryTaste'
+        ip[0] = _TERRITORY_TASTE_ROLES[kw.get('role', 'none')]
+        dp[0] = float(kw.get('rewardAmount', 0))
+        dp[1] = float(kw.get('firstClaimRewardMultiplier', 1.0))
+      elif name == 'Resource':
+        ip[0] = int(kw['initialHealth'])
+        ip[1] = si(kw['destroyedState'])
+        ip[2] = int(kw['rewardDelay'])
+        ip[3] = int(kw.get('delayTillSelfRepair', 15))
+        ip[4] = si('claimed_by_1')
+        ip[5] = si(sm['initialState'])
+        ip[6] = self.groups.index('claimedResources')
+        dp[0] = float(kw['reward']); dp[1] = float(kw['rewardRate'])
+        dp[2] = float(kw.get('selfRepairProbability', 0.1))
+      elif name == 'ResourceClaimer':
+        ip[0] = int(kw['playerIndex']) - 1
+        ip[1], ip[2], ip[3] = int(kw['beamLength']), int(kw['beamRadius']), int(kw['beamWait'])
+        ip[4] = hit_id(f"claimBeam_{int(kw['playerIndex'])}")
+      elif name == 'RewardIndicator':
+        ip[0] = si('inactive')
+        ip[1] = si('dry_claimed_by_1')
+      elif name == 'Paintbrush':
+        ip[0] = int(kw['playerIndex']) - 1
+        ip[1] = hit_id(f"directionHit{int(kw['playerIndex'])}")
+      elif name == 'GraduatedSanctionsMarking':
+        logic = list(kw['hitLogic'])
+        if len(logic) > 3:
+          raise NotImplementedError('GraduatedSanctionsMarking with > 3 levels')
+        ip[0] = int(kw['playerIndex']) - 1
+        ip[1] = si(kw['waitState'])
+        ip[2] = int(kw.get('initialLevel', 1))
+        rec = kw.get('recoveryTime', False)
+        ip[3] = int(rec) if rec else -1
+        ip[4] = hit_id(kw['hitName'])
+        ip[5] = len(logic)
+        ip[6] = si('level_1')
+        for li, lg in enumerate(logic):
+          ip[7 + 3 * li] = int(lg.get('levelIncrement', 0))
+          ip[8 + 3 * li] = int(bool(lg.get('remove', False)))
+          fr = lg.get('freeze', None)
+          ip[9 + 3 * li] = int(fr) if fr else 0
+          dp[2 * li] = float(lg.get('sourceReward', 0))
+          dp[2 * li + 1] = float(lg.get('targetReward', 0))
       elif name == 'DensityRegrow':
         ip[0] = si(kw['liveState'])
         ip[3] = si(kw['waitState'])
@@ -764,6 +838,102 @@ def _commons_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
   sections['ch_nbr'] = nbr
 
 
+def _territory_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
+  """SoA tables for the territory step kernel."""
+  W, P = model.W, model.num_players
+  L = model.layers.index
+  SP = model.sprites.index
+  res = []
+  for oid, ci in _objects_with(model, 'Resource'):
+    kid, x, y, orient, st = model.objects[oid]
+    res.append((oid, y * W + x, kid, ci, st))
+  kid_r, ci_r = res[0][2], res[0][3]
+  if any(r[2] != kid_r for r in res):
+    raise NotImplementedError('heterogeneous resource prefabs')
+  kr = model.kinds[kid_r]
+  rnames = model.state_names[kid_r]
+  rc, rd = model.comps_i[ci_r][1:], model.comps_d[ci_r]
+  if rnames.index('unclaimed') != 0 or rnames.index('destroyed') != 1 or rc[4] != 2:
+    raise NotImplementedError('resource states must be unclaimed, destroyed, claimed_by_1..P')
+  def st_of(kind_name, state):
+    kid = model.kind_names.index(kind_name)
+    return model.states[model.kinds[kid][0] + model.state_names[kid].index(state)]
+  unclaimed = st_of('resource', 'unclaimed')
+  tex = st_of('resource_texture', 'unclaimed')
+  dmg = st_of('damage_indicator', 'damaged')
+  def avatar_comp(comp):
+    rows = []
+    for oid in model.avatar_objs:
+      k = model.kinds[model.objects[oid][0]]
+      ci = [c for c in range(k[2], k[2] + k[3]) if model.comps_i[c][0] == COMP[comp]][0]
+      rows.append((model.comps_i[ci][1:], model.comps_d[ci]))
+    return rows
+  zap = avatar_comp('Zapper')
+  claim = avatar_comp('ResourceClaimer')
+  taste = avatar_comp('TerritoryTaste')
+  for rows, skip in ((zap, ()), (claim, (0, 4)), (taste, ())):
+    for r in rows[1:]:
+      a = [v for i, v in enumerate(r[0]) if i not in skip]; b = [v for i, v in enumerate(rows[0][0]) if i not in skip]
+      if a != b or r[1] != rows[0][1]:
+        raise NotImplementedError('per-avatar beam / taste parameters')
+  zi, zd = zap[0]
+  cli = claim[0][0]
+  ti, td = taste[0]
+  # markings: one per avatar, in avatar order
+  marks = _objects_with(model, 'GraduatedSanctionsMarking')
+  if len(marks) != P:
+    raise NotImplementedError('territory needs one GraduatedSanctionsMarking object per avatar')
+  mk = model.comps_i[marks[0][1]][1:]
+  mkd = model.comps_d[marks[0][1]]
+  for i, (oid, ci) in enumerate(marks):
+    if model.comps_i[ci][1] != i or model.comps_i[ci][2:] != list(model.comps_i[marks[0][1]][2:]):
+      raise NotImplementedError('per-avatar marking parameters')
+  mkind = model.objects[marks[0][0]][0]
+  mnames = model.state_names[mkind]
+  level_states = [model.states[model.kinds[mkind][0] + mnames.index(f'level_{l + 1}')] for l in range(mk[5])]
+  scene_k = model.kinds[model.objects[0][0]]
+  end = [c for c in range(scene_k[2], scene_k[2] + scene_k[3])
+         if model.comps_i[c][0] == COMP['StochasticIntervalEpisodeEnding']][0]
+  ei, ed = model.comps_i[end][1:], model.comps_d[end]
+  hits = {h[0]: (L(h[1]), SP(h[2])) for h in model.hits}
+  ip = np.zeros(64, np.int32)
+  dp = np.zeros(16, np.float64)
+  ip[0:8] = [len(res), unclaimed[0], unclaimed[1], tex[0], tex[1], L('overlay'), dmg[0], dmg[1]]
+  ip[8:12] = [level_states[0][0], mk[2], mk[3], mk[5]]
+  ip[12:18] = [zi[0], zi[1], zi[2], zi[3], zi[4], 0]
+  ip[18:21] = [cli[1], cli[2], cli[3]]
+  ip[21:23] = [hits['zapHit'][0], hits['zapHit'][1]]
+  ip[23] = L('directionIndicatorLayer')
+  ip[24] = L('superDirectionIndicatorLayer')
+  ip[26:28] = [ei[0], ei[1]]
+  ip[28:32] = [rc[0], rc[2], rc[3], ti[0]]
+  for l in range(mk[5]):
+    ip[32 + 4 * l: 36 + 4 * l] = [mk[7 + 3 * l], mk[8 + 3 * l], mk[9 + 3 * l], level_states[l][1]]
+  dp[0:3] = [rd[0], rd[1], rd[2]]
+  dp[3], dp[4] = zd[0], zd[1]
+  dp[5] = ed[0]
+  dp[6], dp[7] = td[0], td[1]
+  for l in range(mk[5]):
+    dp[8 + 2 * l], dp[9 + 2 * l] = mkd[2 * l], mkd[2 * l + 1]
+  sections['tr_ip'] = ip
+  sections['tr_dp'] = dp
+  sections['tr_res'] = np.array([[r[0], r[1], r[4]] for r in res], np.int32)
+  per_player = np.zeros((P, 4), np.int32)
+  ind_kind = model.kind_names.index('reward_indicator')
+  for i in range(P):
+    per_player[i] = [
+        model.states[kr[0] + 2 + i][1],
+        model.states[model.kinds[ind_kind][0] + model.state_names[ind_kind].index(f'dry_claimed_by_{i + 1}')][1],
+        hits[f'directionHit{i + 1}'][1], hits[f'claimBeam_{i + 1}'][1]]
+  sections['tr_player_sprites'] = per_player
+  # cells whose avatar layer is statically blocked by an AllBeamBlocker piece (walls)
+  wall = np.zeros(model.H * W, np.uint8)
+  for oid, ci in _objects_with(model, 'AllBeamBlocker'):
+    kid, x, y, _, _ = model.objects[oid]
+    wall[y * W + x] = 1
+  sections['tr_wall'] = wall
+
+
 # ---------------------------------------------------------------------------
 # Entry points
 # ---------------------------------------------------------------------------
@@ -830,6 +1000,8 @@ def compile_settings(settings: Mapping[str, Any],
     _clean_up_tables(model, sections)
   elif model.family == 'commons_harvest':
     _commons_tables(model, sections)
+  elif model.family == 'territory':
+    _territory_tables(model, sections)
   info = dict(
       level=model.level, family=model.family, layers=model.layers,
       sprites=model.sprites.names, groups=model.groups,

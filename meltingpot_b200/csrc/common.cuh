@@ -64,6 +64,17 @@ struct Tables {
   int avatar_init_group[MP_MAX_PLAYERS];
   const int32_t* spawn_init_cell[2];
   const int32_t* ch_apple;     // [nA][4] obj id, cell, initially live, grass obj id
+  // territory family
+  int nR, nR_pad, res_layer, unclaimed_sprite, tex_layer, tex_sprite, ind_layer, dmg_layer, dmg_sprite, mark_layer;
+  int mark_initial_level, mark_recovery, mark_n_levels, mark_inc[3], mark_remove[3], mark_freeze[3], mark_sprite[3];
+  double mark_src_reward[3], mark_tgt_reward[3];
+  int claim_wait, brush_layer, claim_layer, res_health0, res_reward_delay, res_repair_delay, tr_taste_role;
+  double res_reward, res_rate, res_repair_prob, tr_taste_amount, tr_taste_mult;
+  int claimed_sprite[MP_MAX_PLAYERS], dry_sprite[MP_MAX_PLAYERS], brush_sprite[MP_MAX_PLAYERS], claimbeam_sprite[MP_MAX_PLAYERS];
+  BeamGeom claim_geom, brush_geom;
+  const int32_t* tr_res;       // [nR][3] obj id, cell, initial state
+  const int16_t* res_of_cell;  // [cells_pad] resource index or -1
+  const uint8_t* wall;         // [cells_pad] 1 where an AllBeamBlocker piece stands
   const int32_t* ch_nbr;       // [nA][16] apples inside the regrowth disc (excluding self), -1 padded
   // device tables
   const uint16_t* init_grid;   // [L][cells_pad]
@@ -93,6 +104,10 @@ struct State {
   uint8_t* dirt;
   uint8_t* water;
   uint8_t* apple_count;
+  uint8_t* fam_u8;     // family-specific per-env bytes  [B][fam_u8_stride]
+  uint16_t* fam_u16;   // family-specific per-env shorts [B][fam_u16_stride]
+  int32_t* av_extra;   // i32 [B][P][8] family-specific avatar state
+  int fam_u8_stride, fam_u16_stride;
   int32_t* env;
   // outputs
   double* reward;

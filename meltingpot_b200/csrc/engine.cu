@@ -16,6 +16,7 @@
 #include "render.cuh"
 #include "step_clean_up.cuh"
 #include "step_commons.cuh"
+#include "step_territory.cuh"
 
 namespace {
 
@@ -55,6 +56,8 @@ bool get_section(const void* blob, size_t n, const char* name, int dtype, Sectio
 }
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+constexpr int kMaxAtlasSprites = 96;  // sprites incl. pre-merged ones kept in shared memory by k_render
 
 // Beam footprint in visiting order (policy A.8): centre ray, then for each side the lateral cells
 // outwards, each followed by its forward ray of length `length - k`.
@@ -146,12 +149,12 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   if (m[MPB_META_SPRITE_SIZE] != 8) return fail(MP_E_UNSUPPORTED, "spriteSize %d (kernels are written for 8x8 sprites)", m[MPB_META_SPRITE_SIZE]);
   if (T.P < 1 || T.P > MP_MAX_PLAYERS) return fail(MP_E_UNSUPPORTED, "%d players (max %d)", T.P, MP_MAX_PLAYERS);
   if (T.L > MP_MAX_LAYERS) return fail(MP_E_UNSUPPORTED, "%d layers (max %d)", T.L, MP_MAX_LAYERS);
-  if (T.n_sprites > 256) return fail(MP_E_UNSUPPORTED, "%d sprites (max 256)", T.n_sprites);
+  if (T.n_sprites > kMaxAtlasSprites) return fail(MP_E_UNSUPPORTED, "%d sprites (max %d)", T.n_sprites, kMaxAtlasSprites);
   if (T.n_scalar > 4) return fail(MP_E_UNSUPPORTED, "%d scalar observations (max 4)", T.n_scalar);
   if (T.n_actions < 1) return fail(MP_E_INVALID, "blob has no action table (compile with the substrate config)");
   if (T.cells >= 4096) return fail(MP_E_UNSUPPORTED, "map of %d cells (max 4095)", T.cells);
   for (int k = 0; k < T.n_scalar; ++k) T.scalar_obs[k] = scalar_obs.data[k];
-  if (E->family != MPB_FAMILY_CLEAN_UP && E->family != MPB_FAMILY_COMMONS_HARVEST) return fail(MP_E_UNSUPPORTED, "substrate family %d has no CUDA state-transition kernel yet", E->family);
+  if (E->family != MPB_FAMILY_CLEAN_UP && E->family != MPB_FAMILY_COMMONS_HARVEST && E->family != MPB_FAMILY_TERRITORY) return fail(MP_E_UNSUPPORTED, "substrate family %d has no CUDA state-transition kernel yet", E->family);
 
   // ---- avatars ---------------------------------------------------------------------------------
   T.avatar_layer = av_table.data[2];
@@ -196,7 +199,7 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   // ---- family tables -----------------------------------------------------------------------------
   int rc;
   std::vector<int32_t> v_apple, v_dirt, v_water;
-  T.nA = T.nD = T.nW = 0;
+  T.nA = T.nD = T.nW = 0; T.nR = 0; T.nR_pad = 16;
   T.n_anim = 1; T.anim_frames = 1; T.clean_layer = 0;
   auto zapper = [&](const int32_t* ip) -> int {  // shared Zapper block of cu_ip / ch_ip
     T.zap_cooldown = ip[12]; T.zap_respawn = ip[15]; T.zap_remove = ip[16];
@@ -233,7 +236,7 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
     v_dirt.assign(cu_dirt.data, cu_dirt.data + cu_dirt.count);
     v_water.assign(cu_water.data, cu_water.data + cu_water.count);
     if ((rc = E->upload(v_apple, &T.apple)) || (rc = E->upload(v_dirt, &T.dirt)) || (rc = E->upload(v_water, &T.water))) return rc;
-  } else {  // MPB_FAMILY_COMMONS_HARVEST
+  } else if (E->family == MPB_FAMILY_COMMONS_HARVEST) {
     Section<int32_t> ch_ip, ch_apple, ch_nbr;
     Section<double> ch_dp;
     NEED(ch_ip, MPB_I32) NEED(ch_dp, MPB_F64) NEED(ch_apple, MPB_I32) NEED(ch_nbr, MPB_I32)
@@ -248,6 +251,42 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
     v_apple.assign(ch_apple.data, ch_apple.data + ch_apple.count);
     std::vector<int32_t> v_nbr(ch_nbr.data, ch_nbr.data + ch_nbr.count);
     if ((rc = E->upload(v_apple, &T.ch_apple)) || (rc = E->upload(v_nbr, &T.ch_nbr))) return rc;
+  }
+  else {  // MPB_FAMILY_TERRITORY
+    Section<int32_t> tr_ip, tr_res, tr_player_sprites;
+    Section<double> tr_dp;
+    Section<uint8_t> tr_wall;
+    NEED(tr_ip, MPB_I32) NEED(tr_dp, MPB_F64) NEED(tr_res, MPB_I32) NEED(tr_player_sprites, MPB_I32) NEED(tr_wall, MPB_U8)
+    const int32_t* ip = tr_ip.data; const double* dp = tr_dp.data;
+    T.nR = ip[0]; T.nR_pad = round_up(std::max(T.nR, 64), 16);
+    T.res_layer = ip[1]; T.unclaimed_sprite = ip[2]; T.tex_layer = ip[3]; T.tex_sprite = ip[4]; T.ind_layer = ip[5];
+    T.dmg_layer = ip[6]; T.dmg_sprite = ip[7]; T.mark_layer = ip[8]; T.mark_initial_level = ip[9]; T.mark_recovery = ip[10]; T.mark_n_levels = ip[11];
+    if (T.res_layer != T.avatar_layer) return fail(MP_E_UNSUPPORTED, "territory: resources and avatars must share a layer");
+    if (T.mark_n_levels < 1 || T.mark_n_levels > 3) return fail(MP_E_UNSUPPORTED, "%d marking levels (1..3)", T.mark_n_levels);
+    if ((rc = zapper(ip))) return rc;
+    if (T.zap_respawn <= T.max_frames) return fail(MP_E_UNSUPPORTED, "territory kernel assumes avatars never respawn (framesTillRespawn %d)", T.zap_respawn);
+    if (!make_beam_geom(ip[18], ip[19], &T.claim_geom) || !make_beam_geom(1, 0, &T.brush_geom)) return fail(MP_E_UNSUPPORTED, "beam footprint larger than %d cells", MP_MAX_BEAM_CELLS);
+    T.claim_wait = ip[20]; T.brush_layer = ip[23]; T.claim_layer = ip[24];
+    if (T.claim_layer != T.dmg_layer) return fail(MP_E_UNSUPPORTED, "territory: claim beam layer must be the damage indicator layer");
+    T.res_health0 = ip[28]; T.res_reward_delay = ip[29]; T.res_repair_delay = ip[30]; T.tr_taste_role = ip[31];
+    if (T.tr_taste_role != 0) return fail(MP_E_UNSUPPORTED, "territory Taste roles other than 'none'");
+    if (T.res_health0 < 1 || T.res_health0 > 200) return fail(MP_E_UNSUPPORTED, "resource health %d", T.res_health0);
+    for (int l = 0; l < T.mark_n_levels; ++l) {
+      T.mark_inc[l] = ip[32 + 4 * l]; T.mark_remove[l] = ip[33 + 4 * l]; T.mark_freeze[l] = ip[34 + 4 * l]; T.mark_sprite[l] = ip[35 + 4 * l];
+      T.mark_src_reward[l] = dp[8 + 2 * l]; T.mark_tgt_reward[l] = dp[9 + 2 * l];
+    }
+    T.res_reward = dp[0]; T.res_rate = dp[1]; T.res_repair_prob = dp[2]; T.zap_penalty = dp[3]; T.zap_reward = dp[4]; T.end_prob = dp[5];
+    T.tr_taste_amount = dp[6]; T.tr_taste_mult = dp[7];
+    for (int p = 0; p < T.P; ++p) {
+      const int32_t* ps = tr_player_sprites.data + p * 4;
+      T.claimed_sprite[p] = ps[0]; T.dry_sprite[p] = ps[1]; T.brush_sprite[p] = ps[2]; T.claimbeam_sprite[p] = ps[3];
+    }
+    std::vector<int32_t> v_res(tr_res.data, tr_res.data + tr_res.count);
+    std::vector<int16_t> res_of(T.cells_pad, -1);
+    for (int k = 0; k < T.nR; ++k) res_of[v_res[k * 3 + 1]] = (int16_t)k;
+    std::vector<uint8_t> wall(T.cells_pad, 0);
+    memcpy(wall.data(), tr_wall.data, std::min<size_t>(tr_wall.count, T.cells));
+    if ((rc = E->upload(v_res, &T.tr_res)) || (rc = E->upload(res_of, &T.res_of_cell)) || (rc = E->upload(wall, &T.wall))) return rc;
   }
 #undef NEED
   T.nA_pad = round_up(std::max(T.nA, 1), 16); T.nD_pad = round_up(std::max(std::max(T.nD, T.nA), 1), 16); T.nW_pad = round_up(std::max(T.nW, 1), 16);
@@ -302,7 +341,7 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   auto merged_id = [&](int base, int top) -> int {
     if ((int)pair_of[base].size() <= top) pair_of[base].resize(top + 1, 0);
     if (pair_of[base][top]) return pair_of[base][top];
-    if (n_now() >= 255) return 0;
+    if (n_now() >= kMaxAtlasSprites) return 0;  // budget: the atlas has to fit in shared memory next to the staging buffers
     int id = n_now();
     img.resize((size_t)(id + 1) * 1024);
     for (int f = 0; f < 4; ++f)
@@ -343,6 +382,7 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
       }
     }
     std::vector<int> stack_s, stack_o;
+    for (int pass = 0; pass < 2; ++pass)  // pass 0: the map as it is at reset (most common stacks) gets the budget first
     for (int cell = 0; cell < T.cells; ++cell) {
       // enumerate the cartesian product of per-layer options, bottom up (bounded)
       size_t combos = 1;
@@ -357,11 +397,16 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
       std::vector<int> idx(T.L, 0);
       for (size_t k = 0; k < combos; ++k) {
         stack_s.clear(); stack_o.clear();
+        bool is_initial = true;
         for (int l = 0; l < T.L; ++l) {
           const Opt& op = opts[(size_t)cell * T.L + l];
           const int i = idx[l];
-          if (i < (int)op.sprites.size()) { stack_s.push_back(op.sprites[i]); stack_o.push_back(op.orient); }
+          const int init_v = init_grid.data[(size_t)l * T.cells + cell];
+          const int init_sprite = init_v ? (init_v - 1) >> 2 : -1;
+          if (i < (int)op.sprites.size()) { stack_s.push_back(op.sprites[i]); stack_o.push_back(op.orient); is_initial &= op.sprites[i] == init_sprite; }
+          else is_initial &= init_sprite < 0;
         }
+        if ((pass == 0) != is_initial) stack_s.clear();  // handled in the other pass
         // the walk the kernel performs: opaque bottom, then fold upwards while possible
         int j = -1;
         for (int q = (int)stack_s.size() - 1; q >= 0; --q) if (opq[stack_s[q]]) { j = q; break; }
@@ -435,7 +480,8 @@ int build_plan(mp_engine* E) {
 int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int mode, cudaStream_t st) {
   const int blocks = (E->B + 3) / 4;
   if (E->family == MPB_FAMILY_CLEAN_UP) k_step_clean_up<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
-  else k_step_commons<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
+  else if (E->family == MPB_FAMILY_COMMONS_HARVEST) k_step_commons<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
+  else k_step_territory<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;
@@ -495,8 +541,9 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   State& S = E->S;
   S.B = num_envs; S.seed = seed + env_index_base;
   const size_t B = num_envs, P = T.P;
+  S.fam_u8_stride = std::max(16, RU_COUNT * T.nR_pad); S.fam_u16_stride = std::max(16, RS_COUNT * T.nR_pad);
   if ((rc = E->alloc(B * T.L * T.cells_pad, &S.grid)) || (rc = E->alloc(B * P * 4, &S.avatar)) || (rc = E->alloc(B * P * 4, &S.av_timer)) ||
-      (rc = E->alloc(B * T.nA_pad, &S.apple)) || (rc = E->alloc(B * T.nD_pad, &S.dirt)) || (rc = E->alloc(B * T.nW_pad, &S.water)) || (rc = E->alloc(B * T.nA_pad, &S.apple_count)) || (rc = E->alloc(B * (P + 2), &S.packed)) ||
+      (rc = E->alloc(B * T.nA_pad, &S.apple)) || (rc = E->alloc(B * T.nD_pad, &S.dirt)) || (rc = E->alloc(B * T.nW_pad, &S.water)) || (rc = E->alloc(B * T.nA_pad, &S.apple_count)) || (rc = E->alloc(B * (size_t)S.fam_u8_stride, &S.fam_u8)) || (rc = E->alloc(B * (size_t)S.fam_u16_stride, &S.fam_u16)) || (rc = E->alloc(B * P * 8, &S.av_extra)) || (rc = E->alloc(B * (P + 2), &S.packed)) ||
       (rc = E->alloc(B * ENV_COLS, &S.env)) || (rc = E->alloc(B * P, &S.reward)) || (rc = E->alloc(B, &S.discount)) ||
       (rc = E->alloc(B, &S.step_type)) || (rc = E->alloc(std::max<size_t>(1, T.n_scalar) * B * P, &S.scalar_obs)) ||
       (rc = E->alloc(B * P * E->R.player_bytes, &S.rgb)) || (rc = E->alloc(B * (size_t)E->R.world_bytes, &S.world_rgb)) ||
@@ -511,7 +558,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
     cudaError_t ce = cudaMemcpy(S.env, env0.data(), env0.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) { mp_destroy(E); return fail(MP_E_CUDA, "cudaMemcpy(env) failed: %s", cudaGetErrorString(ce)); }
   }
-  E->step_smem = warp_scratch_bytes(T);
+  E->step_smem = E->family == MPB_FAMILY_TERRITORY ? territory_scratch_bytes(T) : warp_scratch_bytes(T);
   {  // cells per lane per strip: ceil(view_w / 4) for player rows, ceil(W / 8) for world half-rows
     const int ncp = (E->R.view_w + 3) / 4, ncw = (T.W + (32 >> E->R.wstrip_log2) - 1) / (32 >> E->R.wstrip_log2);
     if (ncp <= 3 && ncw <= 3) E->render_fn = k_render<3, 3>;
@@ -522,6 +569,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   cudaError_t ce = cudaFuncSetAttribute(E->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E->R.smem_bytes);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_clean_up, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_commons, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_territory, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
   if (ce != cudaSuccess) { mp_destroy(E); return fail(MP_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)); }
   mp_buffers& bf = E->buffers;
   bf.num_envs = num_envs; bf.num_players = T.P; bf.rgb_h = E->R.view_h * 8; bf.rgb_w = E->R.view_w * 8;

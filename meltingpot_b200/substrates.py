@@ -11,6 +11,7 @@ _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
 PRECOMPILED = {
     'clean_up': (7,),
     'commons_harvest__open': (7, 16),
+    'territory__rooms': (9,),
 }
 
 

@@ -83,7 +83,8 @@ def _ptr(arr, ctype):
   return arr.ctypes.data_as(ctypes.POINTER(ctype))
 
 
-EVENT_NAMES = {1: 'zap', 2: 'edible_consumed', 3: 'player_cleaned'}
+EVENT_NAMES = {1: 'zap', 2: 'edible_consumed', 3: 'player_cleaned', 4: 'claimed_resource',
+               5: 'destroyed_resource', 6: 'sanctioning', 7: 'removal_due_to_sanctioning'}
 
 
 class OracleEnv:

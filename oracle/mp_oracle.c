@@ -77,17 +77,25 @@ typedef struct {
   int player_ate;                                    /* Taste */
   int num_others_cleaned, num_others_ate;            /* AllNonselfCumulants */
   int num_neighbors, dr_started, grass_obj;          /* DensityRegrow */
+  int disallow_zapping, no_zap_counter;              /* Zapper (timed zapping prevention) */
+  int n_connected, connected[4];                     /* Avatar:connect (pieces that move / turn with it) */
+  int health, rewarding_active, claimed_by, never_claimed, destroyed, frames_since_zapped; /* Resource */
+  int texture_obj, damage_obj;                       /* Resource:postStart */
+  int paired_resource;                               /* RewardIndicator */
+  int claim_cool;                                    /* ResourceClaimer */
+  int level, time_not_initial, marking_avatar;       /* GraduatedSanctionsMarking */
 } Obj;
 
-enum { ACT_SET_STATE, ACT_TURN, ACT_MOVE_REL, ACT_TELEPORT_GROUP, ACT_BEAM };
+enum { ACT_SET_STATE, ACT_TURN, ACT_MOVE_REL, ACT_TELEPORT_GROUP, ACT_BEAM, ACT_TELEPORT, ACT_SET_ORIENT };
 typedef struct { int type, obj, a, b, c; } Action;
 
-enum { EV_ZAP = 1, EV_EDIBLE_CONSUMED = 2, EV_PLAYER_CLEANED = 3 };
+enum { EV_ZAP = 1, EV_EDIBLE_CONSUMED = 2, EV_PLAYER_CLEANED = 3, EV_CLAIMED_RESOURCE = 4, EV_DESTROYED_RESOURCE = 5, EV_SANCTIONING = 6, EV_REMOVAL = 7 };
 typedef struct { int type, a, b; } Event;
 
 enum { /* updater function ids */
   UF_AVATAR_MOVE, UF_ZAP, UF_RESPAWN, UF_CLEAN, UF_CLEANER_RESET, UF_TASTE_RESET, UF_NONSELF_GET,
-  UF_NONSELF_RESET, UF_GLOBAL_RESET, UF_EPISODE_END, UF_ANIMATION, UF_SPROUT
+  UF_NONSELF_RESET, UF_GLOBAL_RESET, UF_EPISODE_END, UF_ANIMATION, UF_SPROUT,
+  UF_PAINTBRUSH, UF_CLAIM, UF_PROVIDE_REWARDS, UF_RELEASE_CLAIM, UF_MARKING_RECOVERY
 };
 typedef struct { int priority, comp_type, fn, seq; } Updater;
 
@@ -111,6 +119,7 @@ typedef struct OrEnv {
   /* scene component variables */
   int dirt_count, clean_count, spawner_t, ending_t;
   int cleaned_flag[OR_MAX_PLAYERS], ate_flag[OR_MAX_PLAYERS];
+  uint8_t hit_class[64]; /* 1 = directionHit*, 2 = claimBeam_* */
 } OrEnv;
 
 static const int DX[4] = {0, 1, 0, -1}, DY[4] = {-1, 0, 1, 0}; /* N E S W (component_library.lua:38-43) */
@@ -177,6 +186,82 @@ static void on_enter(OrEnv* e, int target, int initiator) {
   }
 }
 
+/* ---- territory (lua/levels/territory/components.lua, avatar_library.lua:948-1121) ---------------- */
+static int hit_is_direction(const OrEnv* e, int hit); /* 'directionHit*' */
+static int hit_is_claim(const OrEnv* e, int hit);     /* 'claimBeam_*' */
+
+/* Avatar:disallowMovementUntil (avatar_library.lua:475-480), Zapper:disallowZappingUntil (:755-758). */
+static void avatar_disallow_movement_until(Obj* av, int frames) { if (frames > 0) { av->movement_allowed = 0; av->freeze = frames; } }
+static void zapper_disallow_zapping_until(Obj* av, int frames) { av->disallow_zapping = 1; av->no_zap_counter = frames; }
+
+/* Resource:_claim (components.lua:114-131). */
+static void resource_claim(OrEnv* e, int ri, int shooter, const CompDef* c) {
+  Obj* r = &e->obj[ri]; Obj* sh = &e->obj[shooter];
+  const CompDef* av = find_comp(e, sh, MPB_C_AVATAR);
+  r->claimed_by = shooter;
+  int claimed_state = c->ip[4] + av->ip[0];
+  if (r->state != claimed_state && !r->destroyed) {
+    enqueue(e, ACT_SET_STATE, ri, claimed_state, 0, 0);
+    r->rewarding_active = 0;
+    const CompDef* taste = find_comp(e, sh, MPB_C_TERRITORY_TASTE);
+    if (taste && taste->ip[0] != 0) { /* Taste:addRewardIfApplicable :337-346 */
+      double amount = taste->dp[0];
+      if (r->never_claimed) amount = amount * taste->dp[1];
+      avatar_add_reward(e, sh, amount);
+    }
+    r->never_claimed = 0;
+    add_event(e, EV_CLAIMED_RESOURCE, av->ip[0] + 1, 0);
+  }
+}
+/* Resource:onHit (components.lua:133-175). */
+static int resource_on_hit(OrEnv* e, int ri, int shooter, int hit, const CompDef* c) {
+  Obj* r = &e->obj[ri];
+  if (hit_is_direction(e, hit)) resource_claim(e, ri, shooter, c);
+  if (hit_is_claim(e, hit)) { resource_claim(e, ri, shooter, c); return 0; } /* claims pass through resources */
+  const CompDef* z = find_comp(e, &e->obj[shooter], MPB_C_ZAPPER);
+  if (z && hit == z->ip[5]) {
+    r->health -= 1; r->frames_since_zapped = 0;
+    if (r->health == 0) {
+      r->health = c->ip[0];
+      enqueue(e, ACT_SET_STATE, ri, c->ip[1], 0, 0);
+      r->rewarding_active = 0;
+      if (r->texture_obj >= 0) enqueue(e, ACT_SET_STATE, r->texture_obj, c->ip[9], 0, 0);
+      if (r->damage_obj >= 0) enqueue(e, ACT_SET_STATE, r->damage_obj, c->ip[10], 0, 0);
+      add_event(e, EV_DESTROYED_RESOURCE, find_comp(e, &e->obj[shooter], MPB_C_AVATAR)->ip[0] + 1, 0);
+      r->destroyed = 1;
+      return 0; /* zaps pass through a destroyed resource */
+    }
+    return 1;
+  }
+  return 0;
+}
+/* GraduatedSanctionsMarking:onHit (avatar_library.lua:1049-1093). */
+static void marking_on_hit(OrEnv* e, int mi, int shooter, int hit, const CompDef* c) {
+  if (hit != c->ip[4]) return;
+  Obj* mk = &e->obj[mi]; Obj* sh = &e->obj[shooter]; Obj* me = &e->obj[mk->marking_avatar];
+  if (me->layer < 0) return; /* policy A.19: the marking of an avatar that left the grid this frame ignores hits */
+  int l = mk->level - 1;
+  if (l < 0 || l >= c->ip[5]) return;
+  avatar_add_reward(e, sh, c->dp[2 * l]);
+  avatar_add_reward(e, me, c->dp[2 * l + 1]);
+  mk->level += c->ip[7 + 3 * l];
+  const CompDef* sav = find_comp(e, sh, MPB_C_AVATAR); const CompDef* mav = find_comp(e, me, MPB_C_AVATAR);
+  if (c->ip[8 + 3 * l]) { /* remove one frame later (:1058-1069) */
+    me->removal = 1;
+    avatar_disallow_movement_until(me, 1);
+    zapper_disallow_zapping_until(me, 1);
+    add_event(e, EV_REMOVAL, sav->ip[0] + 1, mav->ip[0] + 1);
+  } else {
+    enqueue(e, ACT_SET_STATE, mi, c->ip[6] + mk->level - 1, 0, 0); /* _setLevel */
+    if (c->ip[9 + 3 * l]) { avatar_disallow_movement_until(me, c->ip[9 + 3 * l]); zapper_disallow_zapping_until(me, c->ip[9 + 3 * l]); }
+  }
+  mk->time_not_initial = 0;
+  add_event(e, EV_SANCTIONING, sav->ip[0] + 1, mav->ip[0] + 1);
+}
+
+static int hit_is_direction(const OrEnv* e, int hit) { return hit >= 0 && hit < 64 && e->hit_class[hit] == 1; }
+static int hit_is_claim(const OrEnv* e, int hit) { return hit >= 0 && hit < 64 && e->hit_class[hit] == 2; }
+
 /* GameObject:_onHit: any component returning true blocks the beam (game_object.lua:305-314). */
 static int on_hit(OrEnv* e, int target, int shooter, int hit) {
   Obj* t = &e->obj[target]; Obj* sh = &e->obj[shooter];
@@ -216,6 +301,9 @@ static int on_hit(OrEnv* e, int target, int shooter, int hit) {
           blocked = 1;
         }
         break;
+      case MPB_C_ALL_BEAM_BLOCKER: blocked = 1; break; /* territory/components.lua:46-49 */
+      case MPB_C_RESOURCE: if (resource_on_hit(e, target, shooter, hit, c)) blocked = 1; break;
+      case MPB_C_GRADUATED_SANCTIONS_MARKING: marking_on_hit(e, target, shooter, hit, c); break; /* never blocks */
       default: break;
     }
   }
@@ -267,7 +355,21 @@ static void on_state_change(OrEnv* e, int oi, int old_state) {
         else if (old_state == c->ip[0] && o->state == c->ip[1]) { e->dirt_count--; e->clean_count++; }
         break;
       case MPB_C_AVATAR: /* avatar_library.lua:430-453 */
-        if (old_state == c->ip[2] && o->state == c->ip[1]) { o->freeze = 0; o->removal = 0; }
+        if (old_state == c->ip[2] && o->state == c->ip[1]) {
+          o->freeze = 0; o->removal = 0;
+          for (int k = 0; k < o->n_connected; ++k) { /* avatarStateChange('respawn') :1099-1107 */
+            int mi = o->connected[k]; const CompDef* mc = find_comp(e, &e->obj[mi], MPB_C_GRADUATED_SANCTIONS_MARKING);
+            if (!mc) continue;
+            enqueue(e, ACT_SET_STATE, mi, mc->ip[6] + e->obj[mi].level - 1, 0, 0);
+            enqueue(e, ACT_TELEPORT, mi, o->x, o->y, 0);
+            enqueue(e, ACT_SET_ORIENT, mi, o->orient, 0, 0);
+          }
+        } else if (old_state == c->ip[1] && o->state == c->ip[2]) {
+          for (int k = 0; k < o->n_connected; ++k) { /* avatarStateChange('die') :1108-1110 */
+            int mi = o->connected[k]; const CompDef* mc = find_comp(e, &e->obj[mi], MPB_C_GRADUATED_SANCTIONS_MARKING);
+            if (mc) enqueue(e, ACT_SET_STATE, mi, mc->ip[1], 0, 0);
+          }
+        }
         break;
       case MPB_C_DENSITY_REGROW: /* commons_harvest/components.lua:153-163 */
         if (o->dr_started) {
@@ -336,10 +438,32 @@ static void do_move_rel(OrEnv* e, int oi, int rel) {
   int d = (o->orient + rel) & 3;
   int nx = o->x + DX[d], ny = o->y + DY[d];
   lift(e, oi);
-  if (wrap_or_reject(e, &nx, &ny) && e->grid[o->layer * e->W * e->H + cell_of(e, nx, ny)] == 0) { o->x = nx; o->y = ny; }
+  int ok = wrap_or_reject(e, &nx, &ny) && e->grid[o->layer * e->W * e->H + cell_of(e, nx, ny)] == 0;
+  for (int k = 0; ok && k < o->n_connected; ++k) { /* grid:connect: the group moves only if every member can (policy A.5b) */
+    const Obj* c = &e->obj[o->connected[k]];
+    if (c->layer < 0) continue;
+    int occ = e->grid[c->layer * e->W * e->H + cell_of(e, nx, ny)] - 1;
+    if (occ >= 0 && occ != o->connected[k]) ok = 0;
+  }
+  if (ok) { o->x = nx; o->y = ny; }
   place(e, oi);
+  for (int k = 0; k < o->n_connected; ++k) { /* grid:connect: connected pieces are carried along */
+    Obj* c = &e->obj[o->connected[k]];
+    if (c->layer < 0) continue;
+    lift(e, o->connected[k]); c->x = o->x; c->y = o->y; place(e, o->connected[k]);
+  }
   trigger_enter(e, oi); /* fires even when the move was blocked */
 }
+/* grid:teleport / grid:setOrientation (component_library.lua:331-334). Off-grid pieces have no position. */
+static void do_teleport(OrEnv* e, int oi, int x, int y) {
+  Obj* o = &e->obj[oi];
+  if (o->layer < 0) return;
+  int occ = e->grid[o->layer * e->W * e->H + cell_of(e, x, y)] - 1;
+  if (occ >= 0 && occ != oi) return;
+  lift(e, oi); o->x = x; o->y = y; place(e, oi);
+  trigger_enter(e, oi);
+}
+static void do_set_orient(OrEnv* e, int oi, int orient) { if (e->obj[oi].layer >= 0) e->obj[oi].orient = orient & 3; }
 /* grid:teleportToGroup (component_library.lua:351-354). Policy A.9. */
 static void do_teleport_group(OrEnv* e, int oi, int group, int ns) {
   Obj* o = &e->obj[oi];
@@ -383,7 +507,8 @@ static int beam_cell(OrEnv* e, int shooter, int hit, int x, int y) {
   }
   if (blocked) return 1;
   int hl = e->hits[hit * 2 + MPB_HIT_LAYER], hs = e->hits[hit * 2 + MPB_HIT_SPRITE];
-  if (e->beam[hl * cells + cell] == 0) e->beam[hl * cells + cell] = MPB_CELL(hs, e->obj[shooter].orient);
+  if (e->beam[hl * cells + cell] == 0 && e->grid[hl * cells + cell] == 0) /* only where the hit's layer is free */
+    e->beam[hl * cells + cell] = MPB_CELL(hs, e->obj[shooter].orient);
   return 0;
 }
 /* grid:hitBeam(piece, hit, length, radius) (game_object.lua:253-258); geometry mirrors
@@ -416,6 +541,8 @@ static void process_queue(OrEnv* e) { /* policy A.4: rounds until empty, at most
         case ACT_MOVE_REL: do_move_rel(e, a.obj, a.a); break;
         case ACT_TELEPORT_GROUP: do_teleport_group(e, a.obj, a.a, a.b); break;
         case ACT_BEAM: do_beam(e, a.obj, a.a, a.b, a.c); break;
+        case ACT_TELEPORT: do_teleport(e, a.obj, a.a, a.b); break;
+        case ACT_SET_ORIENT: do_set_orient(e, a.obj, a.a); break;
       }
     }
   }
@@ -431,7 +558,10 @@ static void run_updater(OrEnv* e, const Updater* u, int oi) {
   switch (u->fn) {
     case UF_AVATAR_MOVE: { /* avatar_library.lua:156-171 */
       if (!o->movement_allowed) break;
-      if (o->act[MPB_ACT_TURN] != 0) enqueue(e, ACT_TURN, oi, o->act[MPB_ACT_TURN], 0, 0);
+      if (o->act[MPB_ACT_TURN] != 0) {
+        enqueue(e, ACT_TURN, oi, o->act[MPB_ACT_TURN], 0, 0);
+        for (int k = 0; k < o->n_connected; ++k) enqueue(e, ACT_TURN, o->connected[k], o->act[MPB_ACT_TURN], 0, 0);
+      }
       if (o->act[MPB_ACT_MOVE] != 0) enqueue(e, ACT_MOVE_REL, oi, o->act[MPB_ACT_MOVE] - 1, 0, 0);
     } break;
     case UF_ZAP: { /* avatar_library.lua:613-631 */
@@ -465,6 +595,42 @@ static void run_updater(OrEnv* e, const Updater* u, int oi) {
       if (e->ending_t % c->ip[1] == 0) {
         uint32_t w[4]; rng(e, RS_SCENE, SCENE_DRAW_EPISODE_END, w);
         if (u01(w[0], w[1]) < c->dp[0]) e->cont = 0; /* simulation:endEpisode() */
+      }
+    } break;
+    case UF_PAINTBRUSH: enqueue(e, ACT_BEAM, oi, c->ip[1], 1, 0); break; /* territory/components.lua:401-410 */
+    case UF_CLAIM: { /* ResourceClaimer (components.lua:249-269): no alive check */
+      if (c->ip[3] < 0) break;
+      if (o->claim_cool > 0) o->claim_cool--;
+      else if (o->act[MPB_ACT_FIRE_2] == 1) { o->claim_cool = c->ip[3]; enqueue(e, ACT_BEAM, oi, c->ip[4], c->ip[1], c->ip[2]); }
+    } break;
+    case UF_PROVIDE_REWARDS: { /* components.lua:82-99: group claimedResources, probability rewardRate, startFrame rewardDelay */
+      if (!(state_def(e, o, o->state)->groups & (1u << c->ip[6])) || age < c->ip[2]) break;
+      uint32_t w[4]; rng(e, RS_OBJECT, oi, w);
+      if (!(u01(w[2], w[3]) < c->dp[1])) break;
+      if (o->state != c->ip[1] && o->claimed_by >= 0) {
+        Obj* av = &e->obj[o->claimed_by];
+        const CompDef* taste = find_comp(e, av, MPB_C_TERRITORY_TASTE);
+        if (taste && taste->ip[0] == 2) avatar_add_reward(e, av, 0.0); else avatar_add_reward(e, av, c->dp[0]);
+        o->rewarding_active = 1;
+      }
+    } break;
+    case UF_RELEASE_CLAIM: { /* components.lua:100-112: priority 2, startFrame 5 */
+      if (!(state_def(e, o, o->state)->groups & (1u << c->ip[6])) || age < 5 || o->claimed_by < 0) break;
+      Obj* av = &e->obj[o->claimed_by];
+      if (av->state == find_comp(e, av, MPB_C_AVATAR)->ip[2] && !o->destroyed) {
+        enqueue(e, ACT_SET_STATE, oi, c->ip[5], 0, 0);
+        o->rewarding_active = 0; o->claimed_by = -1;
+      }
+    } break;
+    case UF_MARKING_RECOVERY: { /* avatar_library.lua:1009-1026 */
+      Obj* av = &e->obj[o->marking_avatar];
+      if (o->level != c->ip[2] && avatar_is_alive(e, av)) {
+        o->time_not_initial += 1;
+        if (o->time_not_initial == c->ip[3]) {
+          o->level = c->ip[2];
+          enqueue(e, ACT_SET_STATE, oi, c->ip[6] + o->level - 1, 0, 0);
+          o->time_not_initial = 0;
+        }
       }
     } break;
     case UF_SPROUT: { /* commons_harvest/components.lua:92-123: one updater per wait_k state, priority 10 */
@@ -511,6 +677,10 @@ static void build_updaters(OrEnv* e) {
         case MPB_C_STOCHASTIC_INTERVAL_EPISODE_ENDING: add_updater(e, 100, MPB_C_STOCHASTIC_INTERVAL_EPISODE_ENDING, UF_EPISODE_END); break;
         case MPB_C_ANIMATION: add_updater(e, 100, MPB_C_ANIMATION, UF_ANIMATION); break;
         case MPB_C_DENSITY_REGROW: add_updater(e, 10, MPB_C_DENSITY_REGROW, UF_SPROUT); break;
+        case MPB_C_PAINTBRUSH: add_updater(e, 130, MPB_C_PAINTBRUSH, UF_PAINTBRUSH); break;
+        case MPB_C_RESOURCE_CLAIMER: add_updater(e, 100, MPB_C_RESOURCE_CLAIMER, UF_CLAIM); break;
+        case MPB_C_RESOURCE: add_updater(e, 100, MPB_C_RESOURCE, UF_PROVIDE_REWARDS); add_updater(e, 2, MPB_C_RESOURCE, UF_RELEASE_CLAIM); break;
+        case MPB_C_GRADUATED_SANCTIONS_MARKING: add_updater(e, 3, MPB_C_GRADUATED_SANCTIONS_MARKING, UF_MARKING_RECOVERY); break;
         default: break;
       }
     }
@@ -577,6 +747,31 @@ static void simulation_update(OrEnv* e) {
           o->freeze = o->freeze > 0 ? o->freeze - 1 : 0;
           if (o->removal == 1) enqueue(e, ACT_SET_STATE, oi, c->ip[2], 0, 0);
           o->removal = o->removal > 0 ? o->removal - 1 : 0;
+        } break;
+        case MPB_C_ZAPPER: { /* Zapper:update -- avatar_library.lua:713-724 */
+          if (o->disallow_zapping) o->zap_cool = c->ip[0] + 1;
+          int old_counter = o->no_zap_counter;
+          o->no_zap_counter = o->no_zap_counter > 0 ? o->no_zap_counter - 1 : 0;
+          if (old_counter == 1) o->disallow_zapping = 0;
+        } break;
+        case MPB_C_RESOURCE: { /* Resource:update -- territory/components.lua:184-197 */
+          if (o->health < c->ip[0]) {
+            if (o->damage_obj >= 0) enqueue(e, ACT_SET_STATE, o->damage_obj, c->ip[11], 0, 0);
+            if (o->frames_since_zapped >= c->ip[3]) {
+              uint32_t w[4]; rng(e, RS_OBJECT, oi, w);
+              if (u01(w[0], w[1]) < c->dp[2]) {
+                o->health += 1;
+                if (o->health == c->ip[0] && o->damage_obj >= 0) enqueue(e, ACT_SET_STATE, o->damage_obj, c->ip[10], 0, 0);
+              }
+            }
+            o->frames_since_zapped += 1;
+          }
+        } break;
+        case MPB_C_REWARD_INDICATOR: { /* RewardIndicator:update -- components.lua:303-312 */
+          const Obj* r = &e->obj[o->paired_resource];
+          const CompDef* rc = find_comp(e, r, MPB_C_RESOURCE);
+          if (r->rewarding_active && r->state >= rc->ip[4]) enqueue(e, ACT_SET_STATE, oi, c->ip[1] + (r->state - rc->ip[4]), 0, 0);
+          else enqueue(e, ACT_SET_STATE, oi, c->ip[0], 0, 0);
         } break;
         case MPB_C_DENSITY_REGROW: { /* DensityRegrow:update -> _updateWaitState (commons_harvest/components.lua:147-151,170-193) */
           if (o->layer != c->ip[6] || o->state == c->ip[0]) break;
@@ -654,6 +849,20 @@ static void episode_start(OrEnv* e) {
       if (c->type == MPB_C_ANIMATION && c->ip[11]) { /* component_library.lua:1064-1068 */
         uint32_t w[4]; rng(e, RS_OBJECT_RESET, oi, w);
         enqueue(e, ACT_SET_STATE, oi, c->ip[1 + pick(w[0], (uint32_t)c->ip[0])], 0, 0);
+      } else if (c->type == MPB_C_RESOURCE) { /* Resource:reset / postStart -- components.lua:73-80,177-182 */
+        o->health = c->ip[0]; o->rewarding_active = 0; o->claimed_by = -1; o->never_claimed = 1; o->destroyed = 0; o->frames_since_zapped = 0;
+        o->texture_obj = e->grid[c->ip[7] * (e->W * e->H) + cell_of(e, o->x, o->y)] - 1;
+        o->damage_obj = e->grid[c->ip[8] * (e->W * e->H) + cell_of(e, o->x, o->y)] - 1;
+      } else if (c->type == MPB_C_REWARD_INDICATOR) { /* postStart :288-301 */
+        o->paired_resource = e->grid[c->ip[2] * (e->W * e->H) + cell_of(e, o->x, o->y)] - 1;
+      } else if (c->type == MPB_C_GRADUATED_SANCTIONS_MARKING) { /* reset :985-998, postStart :1033-1047 */
+        o->level = c->ip[2]; o->time_not_initial = 0;
+        o->marking_avatar = e->avatar_obj[c->ip[0]];
+        Obj* av = &e->obj[o->marking_avatar];
+        enqueue(e, ACT_SET_STATE, oi, c->ip[6] + o->level - 1, 0, 0);
+        enqueue(e, ACT_TELEPORT, oi, av->x, av->y, 0);
+        enqueue(e, ACT_SET_ORIENT, oi, av->orient, 0, 0);
+        if (av->n_connected < 4) av->connected[av->n_connected++] = oi;
       } else if (c->type == MPB_C_DENSITY_REGROW) { /* start :139-145, postStart :147-152 */
         o->num_neighbors = 0;
         density_begin_live(e, oi, c);
@@ -751,6 +960,10 @@ OrEnv* oracle_create(const void* blob, size_t n, uint64_t seed) {
     const KindDef* k = &e->kinds[e->objdef[oi * MPB_OBJ_COLS]];
     if (!k->is_avatar) continue;
     for (int i = 0; i < k->n_comps; ++i) if (e->comps[k->comp0 + i].type == MPB_C_AVATAR) e->avatar_obj[e->comps[k->comp0 + i].ip[0]] = oi;
+  }
+  for (int i = 0; i < n_comps; ++i) { /* hit names -> classes (Resource:onHit matches on the name) */
+    if (e->comps[i].type == MPB_C_PAINTBRUSH && e->comps[i].ip[1] < 64) e->hit_class[e->comps[i].ip[1]] = 1;
+    if (e->comps[i].type == MPB_C_RESOURCE_CLAIMER && e->comps[i].ip[4] < 64) e->hit_class[e->comps[i].ip[4]] = 2;
   }
   build_updaters(e);
   e->key[0] = (uint32_t)seed; e->key[1] = (uint32_t)(seed >> 32);

@@ -41,3 +41,9 @@ def commons_blob():
 def commons16_blob():
   from meltingpot_b200 import substrates
   return substrates.load_blob('commons_harvest__open', ('default',) * 16)
+
+
+@pytest.fixture(scope='session')
+def territory_blob():
+  from meltingpot_b200 import substrates
+  return substrates.load_blob('territory__rooms', ('default',) * 9)

@@ -46,8 +46,9 @@ def compare_rollout(blob, oracle, num_envs, steps, seed, check_envs=None, action
       stats['rewards'] += float(rew[b].sum())
       stats['lasts'] += int(st[b] == 2)
       for name, _, _ in e.events():
-        key = {'zap': 'zaps', 'player_cleaned': 'cleaned', 'edible_consumed': 'eaten'}[name]
-        stats[key] += 1
+        key = {'zap': 'zaps', 'player_cleaned': 'cleaned', 'edible_consumed': 'eaten'}.get(name)
+        if key:
+          stats[key] += 1
 
   check(-1, None)
   for t in range(steps):

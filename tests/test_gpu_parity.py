@@ -124,3 +124,19 @@ def test_commons_harvest_16_players(commons16_blob, oracle):
   # BASELINE.json config 3 shape: 16 players (2 inside spawn points + 60 outside).
   stats = parity.compare_rollout(commons16_blob, oracle, num_envs=8, steps=400, seed=11, pixels_every=5)
   assert stats['eaten'] > 50
+
+
+def test_territory_rooms_random_rollout(territory_blob, oracle):
+  # TORUS map, 9 players: claims, zaps on resources, graduated sanctions, removals.
+  stats = parity.compare_rollout(territory_blob, oracle, num_envs=16, steps=600, seed=4, pixels_every=3)
+  assert stats['rewards'] > 50
+
+
+def _zap_heavy(t, B, P, A, rng):
+  probs = np.array([0.05, 0.3, 0.05, 0.05, 0.05, 0.1, 0.1, 0.2, 0.1])
+  return rng.choice(A, size=(B, P), p=probs)
+
+
+def test_territory_rooms_zap_heavy(territory_blob, oracle):
+  stats = parity.compare_rollout(territory_blob, oracle, num_envs=12, steps=500, seed=17, actions_fn=_zap_heavy, pixels_every=5)
+  assert stats['zaps'] > 20
