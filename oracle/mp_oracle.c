@@ -1045,6 +1045,11 @@ void oracle_debug_set_avatar(OrEnv* e, int p, int x, int y, int orient) {
   lift(e, oi); o->x = x; o->y = y; o->orient = orient & 3;
   if (o->layer < 0) { o->state = find_comp(e, o, MPB_C_AVATAR)->ip[1]; o->layer = state_def(e, o, o->state)->layer; }
   place(e, oi);
+  for (int k = 0; k < o->n_connected; ++k) { /* connected pieces (markings) travel with the avatar */
+    Obj* c = &e->obj[o->connected[k]];
+    if (c->layer < 0) continue;
+    lift(e, o->connected[k]); c->x = o->x; c->y = o->y; c->orient = o->orient; place(e, o->connected[k]);
+  }
 }
 void oracle_debug_set_object_state(OrEnv* e, int oi, int state) { do_set_state(e, oi, state); process_queue(e); }
 
