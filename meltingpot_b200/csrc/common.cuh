@@ -141,10 +141,12 @@ __device__ __forceinline__ int dir_dy(int d) { return (d == 2) - (d == 0); }
 __device__ __forceinline__ uint16_t cell_value(int sprite, int orient) { return (uint16_t)(1 + sprite * 4 + (orient & 3)); }
 
 // Maps (x, y) into the map; returns false if it falls outside a BOUNDED map.
+// On a TORUS every caller stays within one map width / height of the map (moves, beam footprints and
+// view windows are all smaller than the map; mp_create checks it), so a conditional add wraps.
 __device__ __forceinline__ bool wrap_or_reject(const Tables& T, int& x, int& y) {
   if (T.topology == 1) {
-    x = x % T.W; if (x < 0) x += T.W;
-    y = y % T.H; if (y < 0) y += T.H;
+    x += x < 0 ? T.W : (x >= T.W ? -T.W : 0);
+    y += y < 0 ? T.H : (y >= T.H ? -T.H : 0);
     return true;
   }
   return x >= 0 && x < T.W && y >= 0 && y < T.H;

@@ -153,6 +153,8 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   if (T.n_scalar > 4) return fail(MP_E_UNSUPPORTED, "%d scalar observations (max 4)", T.n_scalar);
   if (T.n_actions < 1) return fail(MP_E_INVALID, "blob has no action table (compile with the substrate config)");
   if (T.cells >= 4096) return fail(MP_E_UNSUPPORTED, "map of %d cells (max 4095)", T.cells);
+  if (T.topology == 1 && (T.view_l + T.view_r + 1 > T.W || T.view_f + T.view_b + 1 > T.H || T.view_l + T.view_r + 1 > T.H || T.view_f + T.view_b + 1 > T.W))
+    return fail(MP_E_UNSUPPORTED, "TORUS map smaller than the view window");
   for (int k = 0; k < T.n_scalar; ++k) T.scalar_obs[k] = scalar_obs.data[k];
   if (E->family != MPB_FAMILY_CLEAN_UP && E->family != MPB_FAMILY_COMMONS_HARVEST && E->family != MPB_FAMILY_TERRITORY) return fail(MP_E_UNSUPPORTED, "substrate family %d has no CUDA state-transition kernel yet", E->family);
 
@@ -199,6 +201,7 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   // ---- family tables -----------------------------------------------------------------------------
   int rc;
   std::vector<int32_t> v_apple, v_dirt, v_water;
+  std::vector<std::vector<int>> hint_stacks;  // sprite stacks (bottom up) worth a pre-merged sprite before the generic enumeration
   T.nA = T.nD = T.nW = 0; T.nR = 0; T.nR_pad = 16;
   T.n_anim = 1; T.anim_frames = 1; T.clean_layer = 0;
   auto zapper = [&](const int32_t* ip) -> int {  // shared Zapper block of cu_ip / ch_ip
@@ -280,6 +283,10 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
     for (int p = 0; p < T.P; ++p) {
       const int32_t* ps = tr_player_sprites.data + p * 4;
       T.claimed_sprite[p] = ps[0]; T.dry_sprite[p] = ps[1]; T.brush_sprite[p] = ps[2]; T.claimbeam_sprite[p] = ps[3];
+    }
+    for (int p = 0; p < T.P; ++p) {  // wet paint on the resource texture, then dry paint on top: what most resource cells show
+      hint_stacks.push_back({T.tex_sprite, T.claimed_sprite[p]});
+      hint_stacks.push_back({T.tex_sprite, T.claimed_sprite[p], T.dry_sprite[p]});
     }
     std::vector<int32_t> v_res(tr_res.data, tr_res.data + tr_res.count);
     std::vector<int16_t> res_of(T.cells_pad, -1);
@@ -380,6 +387,11 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
           if (s2[MPB_STATE_LAYER] != l || s2[MPB_STATE_SPRITE] < 0) op.absent = true;
         }
       }
+    }
+    for (const auto& hs : hint_stacks) {
+      if (hs.empty() || !opq[hs[0]]) continue;
+      int cur = hs[0];
+      for (size_t q = 1; q < hs.size() && cur; ++q) { if (remapped[hs[q]] || remapped[cur]) break; cur = merged_id(cur, hs[q]); }
     }
     std::vector<int> stack_s, stack_o;
     for (int pass = 0; pass < 2; ++pass)  // pass 0: the map as it is at reset (most common stacks) gets the budget first
