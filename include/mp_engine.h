@@ -110,6 +110,11 @@ int mp_launch_count(mp_handle h, uint64_t* out);
 /* Algorithmic bytes one env-step moves (SURVEY.md section 8d formula), for roofline reports. */
 int mp_algorithmic_bytes(mp_handle h, uint64_t* per_env_step, uint64_t* render_per_env_step);
 
+/* Diagnostic: the renderer's sprite tables. *n_total = atlas sprites including the pre-merged ones;
+ * pair[n_total * n_total] = pre-merged sprite for (bottom, top) or 0; flags[n_total] bit 0 opaque,
+ * bit 1 remapped per viewer. Either array may be NULL (call once for n_total, then again). */
+int mp_debug_render_tables(mp_handle h, int32_t* n_total, uint8_t* pair, uint8_t* flags);
+
 const char* mp_last_error(void);
 const char* mp_version(void);
 

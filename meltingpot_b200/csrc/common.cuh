@@ -90,7 +90,7 @@ struct Tables {
   // render tables
   const uint8_t* atlas;        // [n_total][4][2][8][16]: facing, half (px 0-3 | 4-7), row, 16 B (n_total includes pre-merged sprites)
   const int16_t* sprite_map;   // [P+1][n_total]
-  const uint8_t* sprite_opaque;  // [n_total] 1 = every pixel alpha 255 and never remapped
+  const uint8_t* sprite_opaque;  // [n_total] bit 0: every pixel alpha 255 and never remapped; bit 1: remapped for some viewer
   const uint8_t* sprite_pair;    // [n_total][n_total] pre-merged sprite for (opaque base, sprite on top) or 0
 };
 

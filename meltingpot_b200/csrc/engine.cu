@@ -102,6 +102,7 @@ struct mp_engine {
   size_t step_smem = 0;
   void (*render_fn)(Tables, State, RenderPlan, uint32_t) = nullptr;
   uint64_t algo_bytes = 0, render_bytes = 0;
+  std::vector<uint8_t> host_pair, host_sflags;  // kept for mp_debug_render_tables
 
   template <typename T>
   int upload(const std::vector<T>& host, const T** out) {
@@ -457,7 +458,17 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   std::vector<uint8_t> pair((size_t)n_total * n_total, 0);
   for (int b = 0; b < n_total; ++b)
     for (int t = 0; t < (int)pair_of[b].size(); ++t) pair[(size_t)b * n_total + t] = (uint8_t)pair_of[b][t];
-  if ((rc = E->upload(smap, &T.sprite_map)) || (rc = E->upload(opq, &T.sprite_opaque)) || (rc = E->upload(pair, &T.sprite_pair))) return rc;
+  std::vector<uint8_t> sflags(n_total);  // bit 0 opaque, bit 1 remapped for some viewer, bit 2 binary alpha
+  std::vector<uint8_t> binary_alpha(n_total, 1);  // every alpha 0 or 255
+  for (int i = 0; i < n_total; ++i)
+    for (int px = 0; px < 256; ++px) { const uint8_t a = img[(size_t)i * 1024 + px * 4 + 3]; if (a != 0 && a != 255) { binary_alpha[i] = 0; break; } }
+  for (int i = 0; i < n_total; ++i) {
+    bool bin = true;  // must hold for whatever sprite a viewer sees in its place
+    for (int v = 0; v <= T.P; ++v) bin = bin && binary_alpha[smap[(size_t)v * n_total + i]];
+    sflags[i] = (uint8_t)((opq[i] ? 1 : 0) | (remapped[i] ? 2 : 0) | (bin ? 4 : 0));
+  }
+  E->host_pair = pair; E->host_sflags = sflags;
+  if ((rc = E->upload(smap, &T.sprite_map)) || (rc = E->upload(sflags, &T.sprite_opaque)) || (rc = E->upload(pair, &T.sprite_pair))) return rc;
   return MP_OK;
 }
 
@@ -468,11 +479,11 @@ int build_plan(mp_engine* E) {
   R.player_bytes = R.view_w * R.view_h * 192;
   R.world_bytes = T.H * T.W * 192;
   R.wstrip_log2 = 2;  // 4 pixel rows per WORLD.RGB strip
-  R.stage_bytes = 2 * round_up(std::max(R.view_w * 192, T.W * 24 * (1 << R.wstrip_log2)), 128);
+  R.stage_bytes = RENDER_SLOTS * round_up(std::max(R.view_w * 192, T.W * 24 * (1 << R.wstrip_log2)), 128);
   R.grid_bytes = T.L * T.cells_pad * 2;
   R.n_total = E->n_total;
   R.atlas_bytes = R.n_total * 1024;
-  R.rec_stride = T.L + 1;
+  R.rec_stride = (int)round_up(T.L + 1, 4);  // header + entries, 8-byte aligned records
   R.magic_view_h = (65536u + R.view_h - 1) / R.view_h;
   int off = 128;  // mbarriers
   R.off_atlas = off; off += round_up(R.atlas_bytes, 128);
@@ -671,6 +682,14 @@ int mp_reset_host(mp_handle h, const mp_host_outputs* out, void* stream) {
 int mp_launch_count(mp_handle h, uint64_t* out) {
   if (!h || !out) return fail(MP_E_INVALID, "null argument");
   *out = h->launches;
+  return MP_OK;
+}
+
+int mp_debug_render_tables(mp_handle h, int32_t* n_total, uint8_t* pair, uint8_t* flags) {
+  if (!h) return fail(MP_E_INVALID, "null handle");
+  if (n_total) *n_total = h->n_total;
+  if (pair) memcpy(pair, h->host_pair.data(), h->host_pair.size());
+  if (flags) memcpy(flags, h->host_sflags.data(), h->host_sflags.size());
   return MP_OK;
 }
 

@@ -8,7 +8,7 @@
 //
 // HBM-bound by design: per env-step it reads the ~11 KB sprite grid and writes
 // P*88*88*3 + H*W*192 bytes of observations. One persistent CTA per SM hosts RENDER_TEAMS
-// independent teams of 256 threads that share one shared-memory copy of the sprite atlas
+// independent teams of TEAM_THREADS threads that share one shared-memory copy of the sprite atlas
 // (TMA-bulk-loaded once). Each team renders whole envs:
 //   1. the env's grid arrives by TMA bulk copy behind an mbarrier (prefetched one env ahead);
 //   2. a per-cell pass flattens every cell's layer stack into a short record, folding the opaque
@@ -17,15 +17,27 @@
 //   3. warps pull "cell-row" items (8 pixel rows of one image), compose them in a warp-private
 //      staging buffer (8 pixels = 24 bytes per lane-item) and hand the buffer to cp.async.bulk
 //      shared->global stores, so every observation byte is written once, fully coalesced, by the
-//      copy engine, with no block-wide barrier on the way.
+//      copy engine, with no block-wide barrier on the way. One lane per view cell resolves what the
+//      cell shows to this viewer (a rotated single sprite, or a multi-sprite record) and the eight
+//      lanes that draw its pixel rows fetch that by shuffle; multi-sprite cells are composited by
+//      the lanes that hold them, by selection where every alpha is 0 or 255, arithmetic otherwise.
+// The kernel is bound by instruction latency on the SM (no pipe is saturated), not by HBM: measured
+// with the stores disabled it takes about as long as with them (tools/render_ceiling.py).
 #pragma once
 
 #include <cstdio>
 
 #include "common.cuh"
 
+#ifndef RENDER_TEAMS
 #define RENDER_TEAMS 2
-#define TEAM_THREADS 256
+#endif
+#ifndef TEAM_THREADS
+#define TEAM_THREADS 384
+#endif
+#ifndef RENDER_SLOTS
+#define RENDER_SLOTS 1  // staging slots per warp (24 warps per SM hide the TMA read of a single slot)
+#endif
 #define RENDER_THREADS (RENDER_TEAMS * TEAM_THREADS)
 
 struct RenderPlan {  // host-computed constants of the tiling
@@ -96,10 +108,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(TEAM_THREADS) : "memory"); }
 
 // dst, src: R | G<<8 | B<<16 (| A<<24 for src). Integer "over": (s*a + d*(255-a)) / 255, truncated.
+// Branch free on purpose: a == 255 yields src and a == 0 yields dst exactly, so opaque sprites and
+// empty pixels need no special case (and no divergence).
 __device__ __forceinline__ uint32_t blend_px(uint32_t dst, uint32_t src) {
   const uint32_t a = src >> 24;
-  if (a == 255u) return src;
-  if (a == 0u) return dst;
   const uint32_t ia = 255u - a;
   uint32_t rb = (src & 0x00FF00FFu) * a + (dst & 0x00FF00FFu) * ia;  // two 16-bit lanes, each <= 65025
   uint32_t g = ((src >> 8) & 0xFFu) * a + ((dst >> 8) & 0xFFu) * ia;
@@ -108,24 +120,86 @@ __device__ __forceinline__ uint32_t blend_px(uint32_t dst, uint32_t src) {
   return rb | (g << 8);
 }
 
-// Composites pixel row `py` of a flattened cell record into px[8], bottom up.
-__device__ __forceinline__ void compose_record(uint32_t px[8], const uint8_t* __restrict__ s_atlas, const uint16_t* __restrict__ rec,
-                                               const int16_t* __restrict__ s_map, const uint8_t* __restrict__ opaque,
-                                               int viewer_orient, int py) {
+// Record entry: bits 0-12 sprite * 4 + orientation, then the sprite's flag byte shifted by 13:
+// bit 13 = opaque, bit 14 = remapped for some viewer (look it up in the viewer's sprite map),
+// bit 15 = every alpha is 0 or 255 for every viewer (composited by selection instead of arithmetic).
+#define ENT_SHIFT 13
+#define ENT_VALUE 0x1fff
+#define ENT_OPAQUE 0x2000
+#define ENT_REMAP 0x4000
+#define ENT_BINARY 0x8000
+
+__device__ __forceinline__ uint32_t select_px(uint32_t dst, uint32_t src) { return (int32_t)src < 0 ? src : dst; }  // alpha in {0, 255}
+
+// Composites pixel row `py` of a multi-sprite record over px[8] (bottom up). Lane private: lanes of a
+// warp that hold such cells run their chains side by side (the kernel is latency bound, not issue bound).
+__device__ __forceinline__ void compose_row(uint32_t px[8], const uint8_t* __restrict__ s_atlas, const uint16_t* __restrict__ rec,
+                                            const int16_t* __restrict__ s_map, int viewer_orient, int py) {
   const int n = rec[0];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) px[k] = 0;
   for (int k = 1; k <= n; ++k) {
-    const int v = (int)rec[k] - 1;
-    const int sprite = s_map[v >> 2];
-    const int facing = ((v & 3) - viewer_orient) & 3;
+    const uint32_t e = rec[k];
+    int sprite = (e & ENT_VALUE) >> 2;
+    if (e & ENT_REMAP) sprite = s_map[sprite];
+    const int facing = ((int)(e & 3) - viewer_orient) & 3;
     const uint8_t* t = s_atlas + (sprite * 4 + facing) * 256 + py * 16;
     const uint4 lo = *reinterpret_cast<const uint4*>(t);
     const uint4 hi = *reinterpret_cast<const uint4*>(t + 128);
-    if (opaque[sprite]) {
-      px[0] = lo.x; px[1] = lo.y; px[2] = lo.z; px[3] = lo.w; px[4] = hi.x; px[5] = hi.y; px[6] = hi.z; px[7] = hi.w;
+    if (e & ENT_BINARY) {
+      px[0] = select_px(px[0], lo.x); px[1] = select_px(px[1], lo.y); px[2] = select_px(px[2], lo.z); px[3] = select_px(px[3], lo.w);
+      px[4] = select_px(px[4], hi.x); px[5] = select_px(px[5], hi.y); px[6] = select_px(px[6], hi.z); px[7] = select_px(px[7], hi.w);
     } else {
       px[0] = blend_px(px[0], lo.x); px[1] = blend_px(px[1], lo.y); px[2] = blend_px(px[2], lo.z); px[3] = blend_px(px[3], lo.w);
       px[4] = blend_px(px[4], hi.x); px[5] = blend_px(px[5], hi.y); px[6] = blend_px(px[6], hi.z); px[7] = blend_px(px[7], hi.w);
     }
+  }
+}
+
+// Header of a flattened cell record: bit 15 set = the cell is a single opaque sprite and the low
+// bits are sprite * 4 + orientation (fast path); otherwise the number of entries that follow.
+#define REC_FAST 0x8000
+
+// Per-cell pass of one env: flattens each cell's layer stack into a record, folding map sprites into
+// pre-merged ones. LMAX >= T.L is a compile-time bound so that the layer loads are independent and
+// unrolled; the layers that matter are then found with bit masks (most cells hold one sprite).
+template <int LMAX>
+__device__ __forceinline__ void cell_pass(const Tables& T, const RenderPlan& R, const uint16_t* __restrict__ s_grid, uint16_t* __restrict__ s_rec,
+                                          const uint8_t* __restrict__ s_flags, const uint8_t* __restrict__ s_pair, int ttid, uint32_t dbg) {
+  for (int c = ttid; c < T.cells; c += TEAM_THREADS) {
+    uint32_t v[LMAX];
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) v[l] = l < T.L ? s_grid[l * T.cells_pad + c] : 0u;
+    uint32_t nz = 0, oq = 0;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      const uint32_t f = v[l] ? s_flags[(v[l] - 1) >> 2] : 0u;
+      nz |= (v[l] ? 1u : 0u) << l;
+      oq |= (f & 1u) << l;
+    }
+    oq &= ~1u;
+    const int lo = oq ? 31 - __clz(oq) : 0;  // the topmost opaque layer hides everything below it
+    uint32_t cand = nz & (0xffffffffu << lo);
+    uint16_t* r = s_rec + c * R.rec_stride;
+    int n = 0;
+    uint32_t cur = 0, cf = 0;
+    bool merging = true;
+    while (cand) {
+      const int l = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const uint32_t vl = s_grid[l * T.cells_pad + c];
+      if (cur == 0) { cur = vl; cf = s_flags[(vl - 1) >> 2]; continue; }
+      if (merging) {
+        const uint32_t m = s_pair[((cur - 1) >> 2) * R.n_total + ((vl - 1) >> 2)];
+        if (m && (((cur - 1) ^ (vl - 1)) & 3u) == 0) { cur = 1 + m * 4 + ((vl - 1) & 3u); cf = 5; continue; }  // merged sprites: opaque, binary
+        merging = false;
+      }
+      r[1 + n++] = (uint16_t)((cur - 1) | (cf << ENT_SHIFT));
+      cur = vl; cf = s_flags[(vl - 1) >> 2];
+    }
+    if (cur) r[1 + n++] = (uint16_t)((cur - 1) | (cf << ENT_SHIFT));
+    if ((n == 1 && (cf & 1u)) || ((dbg & 256u) && cur)) r[0] = (uint16_t)(REC_FAST | (cur - 1));  // (bit 8: debug -- top sprite only)
+    else r[0] = (uint16_t)n;
   }
 }
 
@@ -146,14 +220,9 @@ __device__ __forceinline__ void store_row(uint8_t* dst, const uint32_t px[8]) {
   d[0] = a; d[1] = b; d[2] = c;
 }
 
-// Header of a flattened cell record: bit 15 set = the cell is a single opaque sprite and the low
-// bits are sprite * 4 + orientation (fast path); otherwise the number of entries that follow.
-#define REC_FAST 0x8000
-
-// Loads pixel row `py` of the sprite variant selected by a fast-path header.
-__device__ __forceinline__ void fast_row(uint32_t px[8], const uint8_t* __restrict__ s_atlas, int h, int viewer_orient, int py) {
-  const int v = h & 0x7fff;
-  const uint8_t* t = s_atlas + ((v & ~3) | (((v & 3) - viewer_orient) & 3)) * 256 + py * 16;
+// Loads pixel row `py` of the sprite variant (sprite * 4 + facing) selected by a fast-path header.
+__device__ __forceinline__ void fast_row(uint32_t px[8], const uint8_t* __restrict__ s_atlas, int h, int py) {
+  const uint8_t* t = s_atlas + (h & 0x7fff) * 256 + py * 16;
   const uint4 lo = *reinterpret_cast<const uint4*>(t);
   const uint4 hi = *reinterpret_cast<const uint4*>(t + 128);
   px[0] = lo.x; px[1] = lo.y; px[2] = lo.z; px[3] = lo.w; px[4] = hi.x; px[5] = hi.y; px[6] = hi.z; px[7] = hi.w;
@@ -217,7 +286,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
   const int n_items = n_player_items + ((flags & 1u) ? (8 >> wlog) * T.H : 0);
   const int prow_bytes = R.view_w * 24, wrow_bytes = T.W * 24;
   const int pitem_bytes = prow_bytes * 8, witem_bytes = wrow_bytes * wrows;
-  const int slot_bytes = R.stage_bytes >> 1;
+  const int slot_bytes = R.stage_bytes / RENDER_SLOTS;
   const int h_oob = REC_FAST | (T.oob_sprite * 4), h_oov = REC_FAST | (T.oov_sprite * 4);
   const uint64_t store_policy = make_evict_first_policy();
   uint32_t slot = 0;
@@ -232,30 +301,11 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
     }
     mbar_wait(gbar, (uint32_t)(it & 1));
     // ---- per-cell pass: flatten the layer stack, folding map sprites into pre-merged ones -------
-    for (int c = ttid; c < T.cells; c += TEAM_THREADS) {
-      int lo = 0;
-      for (int l = T.L - 1; l > 0; --l) {
-        const int v = s_grid[l * T.cells_pad + c];
-        if (v && s_opaque[(v - 1) >> 2]) { lo = l; break; }
-      }
-      uint16_t* r = s_rec + c * R.rec_stride;
-      int n = 0, cur = 0;
-      bool merging = true;
-      for (int l = lo; l < T.L; ++l) {
-        const int v = s_grid[l * T.cells_pad + c];
-        if (!v) continue;
-        if (cur == 0) { cur = v; continue; }
-        if (merging) {
-          const int m = s_pair[((cur - 1) >> 2) * R.n_total + ((v - 1) >> 2)];
-          if (m && (((cur - 1) ^ (v - 1)) & 3) == 0) { cur = 1 + m * 4 + ((v - 1) & 3); continue; }
-          merging = false;
-        }
-        r[1 + n++] = (uint16_t)cur;
-        cur = v;
-      }
-      if (cur) r[1 + n++] = (uint16_t)cur;
-      if (n == 1 && s_opaque[(cur - 1) >> 2]) r[0] = (uint16_t)(REC_FAST | (cur - 1));
-      else r[0] = (uint16_t)n;
+    if (!(flags & 64u) || it == 0) {  // (bit 6: debug -- reuse the first env's records)
+      if (T.L <= 8) cell_pass<8>(T, R, s_grid, s_rec, s_opaque, s_pair, ttid, flags);
+      else if (T.L <= 10) cell_pass<10>(T, R, s_grid, s_rec, s_opaque, s_pair, ttid, flags);
+      else if (T.L <= 12) cell_pass<12>(T, R, s_grid, s_rec, s_opaque, s_pair, ttid, flags);
+      else cell_pass<MP_MAX_LAYERS>(T, R, s_grid, s_rec, s_opaque, s_pair, ttid, flags);
     }
     team_sync(team);  // records complete; the grid buffer is free again
     const int nb = b + n_streams;
@@ -270,9 +320,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
       if (lane == 0) item = atomicAdd(&s_next_item[team], 1);
       item = __shfl_sync(MP_FULL, item, 0);
       if (item >= n_items) break;
-      uint8_t* buf = s_stage + (slot & 1) * slot_bytes;
+      uint8_t* buf = s_stage + (slot % RENDER_SLOTS) * slot_bytes;
       ++slot;
-      if (lane == 0) bulk_wait_read<1>();  // the store that last used this slot has drained
+      if (lane == 0) bulk_wait_read<RENDER_SLOTS - 1>();  // the store that last used this slot has drained
       __syncwarp();
       if (item < n_player_items) {
         const int p = (int)(((uint32_t)item * R.magic_view_h) >> 16), cy = item - p * R.view_h;
@@ -282,36 +332,37 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
         const int df = T.view_f - cy;
         const int bx = vi.ax + vi.fdx * df - vi.rdx * T.view_l, by = vi.ay + vi.fdy * df - vi.rdy * T.view_l;
         int hdr[NCP];
-        const uint16_t* rec[NCP];
         uint32_t px[NCP][8];
         if (!(flags & 16u)) {  // (bit 4: debug / ceiling measurement -- issue the stores without composing)
-#pragma unroll
-        for (int i = 0; i < NCP; ++i) {  // headers of all my cells first ...
-          const int cx = cg + 4 * i;
-          int wx = bx + vi.rdx * cx, wy = by + vi.rdy * cx;
-          const bool inb = wrap_or_reject(T, wx, wy);
-          rec[i] = s_rec + (inb ? (wy * T.W + wx) : 0) * R.rec_stride;
-          const int h = rec[i][0];
-          hdr[i] = !vi.alive ? (h_oov | vi.ao) : (inb ? h : (h_oob | vi.ao));  // policy A.13
-        }
-#pragma unroll
-        for (int i = 0; i < NCP; ++i) {  // ... then their sprite rows ...
-          if (hdr[i] & REC_FAST) fast_row(px[i], s_atlas, hdr[i], vi.ao, py);
-          else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) px[i][k] = 0;
-            compose_record(px[i], s_atlas, rec[i], map, s_opaque, vi.ao, py);
+        // lane cx resolves view cell cx once: a single-sprite cell becomes REC_FAST | sprite * 4 + facing as this
+        // viewer sees it, anything else the cell index; the 8 lanes that draw the cell's rows fetch it by shuffle
+        int myh = h_oov;
+        if (lane < R.view_w && vi.alive) {
+          int wx = bx + vi.rdx * lane, wy = by + vi.rdy * lane;
+          if (wrap_or_reject(T, wx, wy)) {
+            const int cell = wy * T.W + wx, h = s_rec[cell * R.rec_stride];
+            myh = (h & REC_FAST) ? ((h & ~3) | ((h - vi.ao) & 3)) : cell;
+          } else {
+            myh = h_oob;  // policy A.13
           }
         }
 #pragma unroll
-        for (int i = 0; i < NCP; ++i) {  // ... then pack and stage
+        for (int i = 0; i < NCP; ++i) hdr[i] = __shfl_sync(MP_FULL, myh, cg + 4 * i);
+#pragma unroll
+        for (int i = 0; i < NCP; ++i)  // ... then a sprite row for every cell (a multi-sprite cell loads a dummy: no branch yet) ...
+          fast_row(px[i], s_atlas, (hdr[i] & REC_FAST) ? hdr[i] : 0, py);
+#pragma unroll
+        for (int i = 0; i < NCP; ++i)  // ... multi-sprite cells are composited by the lanes that hold them ...
+          if (!(hdr[i] & REC_FAST)) compose_row(px[i], s_atlas, s_rec + hdr[i] * R.rec_stride, map, vi.ao, py);
+#pragma unroll
+        for (int i = 0; i < NCP; ++i) {  // ... pack and stage
           const int cx = cg + 4 * i;
           if (cx < R.view_w) store_row(buf + py * prow_bytes + cx * 24, px[i]);
         }
         }
-        fence_async_smem();  // make this lane's writes visible to the async (TMA) proxy
+        if (!(flags & 128u)) fence_async_smem();  // make this lane's writes visible to the async (TMA) proxy
         __syncwarp();
-        if (lane == 0) bulk_store(S.rgb + ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * pitem_bytes, buf, (uint32_t)pitem_bytes, store_policy);
+        if (lane == 0 && !(flags & 32u)) bulk_store(S.rgb + ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * pitem_bytes, buf, (uint32_t)pitem_bytes, store_policy);
       } else {
         const int wi = item - n_player_items, wy = wi >> (3 - wlog);
         const int py = ((wi & ((8 >> wlog) - 1)) << wlog) | (lane & (wrows - 1)), cg = lane >> wlog;
@@ -323,18 +374,15 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
         if (!(flags & 16u)) {
 #pragma unroll
         for (int i = 0; i < NCW; ++i) {
-          const int cx = min(cg + cstep * i, T.W - 1);
-          hdr[i] = rowrec[cx * R.rec_stride];
+          const int cx = cg + cstep * i;
+          hdr[i] = cx < T.W ? (int)rowrec[cx * R.rec_stride] : h_oov;
         }
+#pragma unroll
+        for (int i = 0; i < NCW; ++i) fast_row(px[i], s_atlas, (hdr[i] & REC_FAST) ? hdr[i] : 0, py);
 #pragma unroll
         for (int i = 0; i < NCW; ++i) {
           const int cx = min(cg + cstep * i, T.W - 1);
-          if (hdr[i] & REC_FAST) fast_row(px[i], s_atlas, hdr[i], 0, py);
-          else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) px[i][k] = 0;
-            compose_record(px[i], s_atlas, rowrec + cx * R.rec_stride, map, s_opaque, 0, py);
-          }
+          if (!(hdr[i] & REC_FAST)) compose_row(px[i], s_atlas, rowrec + cx * R.rec_stride, map, 0, py);
         }
 #pragma unroll
         for (int i = 0; i < NCW; ++i) {
@@ -342,9 +390,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
           if (cx < T.W) store_row(buf + (py & (wrows - 1)) * wrow_bytes + cx * 24, px[i]);
         }
         }
-        fence_async_smem();
+        if (!(flags & 128u)) fence_async_smem();
         __syncwarp();
-        if (lane == 0) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wi * witem_bytes, buf, (uint32_t)witem_bytes, store_policy);
+        if (lane == 0 && !(flags & 32u)) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wi * witem_bytes, buf, (uint32_t)witem_bytes, store_policy);
       }
     }
     team_sync(team);  // every warp is done with s_rec / s_view

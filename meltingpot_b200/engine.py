@@ -23,7 +23,7 @@ MP_FLAG_DEFAULT = 3
 EXPORTED_SYMBOLS = (
     'mp_create', 'mp_destroy', 'mp_set_flags', 'mp_reset', 'mp_step',
     'mp_step_state', 'mp_render', 'mp_get_buffers', 'mp_step_host',
-    'mp_reset_host', 'mp_launch_count', 'mp_algorithmic_bytes',
+    'mp_reset_host', 'mp_launch_count', 'mp_algorithmic_bytes', 'mp_debug_render_tables',
     'mp_last_error', 'mp_version',
 )
 
@@ -81,6 +81,7 @@ def load_library() -> ctypes.CDLL:
   lib.mp_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
   lib.mp_algorithmic_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64),
                                        ctypes.POINTER(ctypes.c_uint64)]
+  lib.mp_debug_render_tables.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), vp, vp]
   lib.mp_last_error.restype = ctypes.c_char_p
   lib.mp_version.restype = ctypes.c_char_p
   _lib = lib
@@ -244,6 +245,16 @@ class Engine:
     n = ctypes.c_uint64(0)
     _check(self._lib.mp_launch_count(self._h, ctypes.byref(n)))
     return int(n.value)
+
+  def render_tables(self):
+    """(pair[n, n], flags[n]) uint8 numpy arrays of the renderer's sprite tables (diagnostic)."""
+    import numpy as np
+    n = ctypes.c_int32(0)
+    _check(self._lib.mp_debug_render_tables(self._h, ctypes.byref(n), None, None))
+    pair = np.zeros((n.value, n.value), np.uint8)
+    flags = np.zeros((n.value,), np.uint8)
+    _check(self._lib.mp_debug_render_tables(self._h, ctypes.byref(n), pair.ctypes.data, flags.ctypes.data))
+    return pair, flags
 
   def algorithmic_bytes(self):
     a, r = ctypes.c_uint64(0), ctypes.c_uint64(0)

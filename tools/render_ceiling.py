@@ -21,9 +21,14 @@ gen = torch.Generator(device='cuda').manual_seed(0)
 for t in range(steps):
   eng.step_state(torch.randint(0, eng.num_actions, (B, players), generator=gen, device='cuda', dtype=torch.int32))
 full = timeit(eng.render)
-eng.set_flags(3 | 16); stores = timeit(eng.render); eng.set_flags(3)
+eng.set_flags(3 | 16); stores = timeit(eng.render)
+eng.set_flags(3 | 32); compute = timeit(eng.render)
+extra = {}
+for nm, fl in (('neither', 48), ('compose_nocellpass', 32 | 64), ('compose_nofence', 32 | 128), ('neither_nocellpass', 48 | 64), ('compose_allfast', 32 | 256), ('allfast', 256)):
+  eng.set_flags((3 if fl > 3 else 0) | fl); extra[nm] = round(timeit(eng.render), 4)
+eng.set_flags(3)
 grid = eng.grid.view(torch.int16)
 occupied = (grid != 0).float().sum(1)  # layers occupied per cell
-print(json.dumps({'substrate': name, 'envs': B, 'after_steps': steps, 'render_ms': full, 'stores_only_ms': stores,
+print(json.dumps({'substrate': name, 'envs': B, 'after_steps': steps, 'render_ms': full, 'stores_only_ms': stores, 'compose_only_ms': compute, 'extra': extra,
                   'mean_layers_per_cell': float(occupied.mean()), 'cells_with_3plus_layers': float((occupied >= 3).float().mean()),
                   'alive': float(eng.avatar_state[:, :, 3].float().mean())}))
