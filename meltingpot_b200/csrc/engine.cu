@@ -513,7 +513,14 @@ int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int 
 int launch_render(mp_engine* E, cudaStream_t st) {
   if (!(E->flags & (MP_FLAG_RENDER_WORLD | MP_FLAG_RENDER_PLAYERS))) return MP_OK;
   const int blocks = std::min((E->B + RENDER_TEAMS - 1) / RENDER_TEAMS, E->sm_count);
-  E->render_fn<<<blocks, RENDER_THREADS, E->R.smem_bytes, st>>>(E->T, E->S, E->R, E->flags);
+  RenderPlan R = E->R;
+  const Tables& T = E->T;
+  R.n_player_items = (E->flags & MP_FLAG_RENDER_PLAYERS) ? T.P * R.view_h : 0;
+  R.n_items = R.n_player_items + ((E->flags & MP_FLAG_RENDER_WORLD) ? (8 >> R.wstrip_log2) * T.H : 0);
+  R.prow_bytes = R.view_w * 24; R.wrow_bytes = T.W * 24;
+  R.pitem_bytes = R.prow_bytes * 8; R.witem_bytes = R.wrow_bytes << R.wstrip_log2;
+  R.h_oob = 0x8000 | (T.oob_sprite * 4); R.h_oov = 0x8000 | (T.oov_sprite * 4);
+  E->render_fn<<<blocks, RENDER_THREADS, R.smem_bytes, st>>>(E->T, E->S, R, E->flags);
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;

@@ -33,10 +33,10 @@
 #define RENDER_TEAMS 2
 #endif
 #ifndef TEAM_THREADS
-#define TEAM_THREADS 384
+#define TEAM_THREADS 512
 #endif
 #ifndef RENDER_SLOTS
-#define RENDER_SLOTS 1  // staging slots per warp (24 warps per SM hide the TMA read of a single slot)
+#define RENDER_SLOTS 1  // staging slots per warp (32 warps per SM hide the TMA read of a single slot)
 #endif
 #define RENDER_THREADS (RENDER_TEAMS * TEAM_THREADS)
 
@@ -55,6 +55,11 @@ struct RenderPlan {  // host-computed constants of the tiling
   int wstrip_log2;                      // log2 of the pixel rows per WORLD.RGB strip (1 or 2)
   int stage_bytes;                      // warp-private staging buffer: two slots, each one player cell-row or half a world cell-row
   int smem_bytes;
+  // per-launch constants (depend on the render flags); kept here so that they are constant-bank operands, not registers
+  int n_player_items, n_items;           // strips per env: player cell-rows, then WORLD.RGB strips
+  int prow_bytes, wrow_bytes;            // one pixel row of a player image / of WORLD.RGB
+  int pitem_bytes, witem_bytes;          // one strip
+  int h_oob, h_oov;                      // fast-path headers of the OutOfBounds / OutOfView sprites
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -281,13 +286,8 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
   mbar_wait(&bar[0], 0);
   if (first >= S.B) return;
 
-  const int n_player_items = (flags & 2u) ? T.P * R.view_h : 0;
   const int wlog = R.wstrip_log2, wrows = 1 << wlog;  // pixel rows per WORLD.RGB strip (2 or 4)
-  const int n_items = n_player_items + ((flags & 1u) ? (8 >> wlog) * T.H : 0);
-  const int prow_bytes = R.view_w * 24, wrow_bytes = T.W * 24;
-  const int pitem_bytes = prow_bytes * 8, witem_bytes = wrow_bytes * wrows;
   const int slot_bytes = R.stage_bytes / RENDER_SLOTS;
-  const int h_oob = REC_FAST | (T.oob_sprite * 4), h_oov = REC_FAST | (T.oov_sprite * 4);
   const uint64_t store_policy = make_evict_first_policy();
   uint32_t slot = 0;
   int it = 0;
@@ -315,16 +315,25 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
     }
 
     // ---- strip items, pulled by warps -------------------------------------------------------------
+#ifndef MP_V_NOPREFETCH
+    int next_item = 0;  // claimed one strip ahead so that the atomic's latency hides behind the strip being drawn
+    if (lane == 0) next_item = atomicAdd(&s_next_item[team], 1);
+    for (;;) {
+      const int item = __shfl_sync(MP_FULL, next_item, 0);
+      if (item >= R.n_items) break;
+      if (lane == 0) next_item = atomicAdd(&s_next_item[team], 1);
+#else
     for (;;) {
       int item = 0;
       if (lane == 0) item = atomicAdd(&s_next_item[team], 1);
       item = __shfl_sync(MP_FULL, item, 0);
-      if (item >= n_items) break;
+      if (item >= R.n_items) break;
+#endif
       uint8_t* buf = s_stage + (slot % RENDER_SLOTS) * slot_bytes;
       ++slot;
       if (lane == 0) bulk_wait_read<RENDER_SLOTS - 1>();  // the store that last used this slot has drained
       __syncwarp();
-      if (item < n_player_items) {
+      if (item < R.n_player_items) {
         const int p = (int)(((uint32_t)item * R.magic_view_h) >> 16), cy = item - p * R.view_h;
         const ViewerInfo vi = s_view[p];
         const int16_t* map = s_map + p * R.n_total;
@@ -332,67 +341,58 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
         const int df = T.view_f - cy;
         const int bx = vi.ax + vi.fdx * df - vi.rdx * T.view_l, by = vi.ay + vi.fdy * df - vi.rdy * T.view_l;
         int hdr[NCP];
-        uint32_t px[NCP][8];
         if (!(flags & 16u)) {  // (bit 4: debug / ceiling measurement -- issue the stores without composing)
         // lane cx resolves view cell cx once: a single-sprite cell becomes REC_FAST | sprite * 4 + facing as this
         // viewer sees it, anything else the cell index; the 8 lanes that draw the cell's rows fetch it by shuffle
-        int myh = h_oov;
+        int myh = R.h_oov;
         if (lane < R.view_w && vi.alive) {
           int wx = bx + vi.rdx * lane, wy = by + vi.rdy * lane;
           if (wrap_or_reject(T, wx, wy)) {
             const int cell = wy * T.W + wx, h = s_rec[cell * R.rec_stride];
             myh = (h & REC_FAST) ? ((h & ~3) | ((h - vi.ao) & 3)) : cell;
           } else {
-            myh = h_oob;  // policy A.13
+            myh = R.h_oob;  // policy A.13
           }
         }
 #pragma unroll
         for (int i = 0; i < NCP; ++i) hdr[i] = __shfl_sync(MP_FULL, myh, cg + 4 * i);
 #pragma unroll
-        for (int i = 0; i < NCP; ++i)  // ... then a sprite row for every cell (a multi-sprite cell loads a dummy: no branch yet) ...
-          fast_row(px[i], s_atlas, (hdr[i] & REC_FAST) ? hdr[i] : 0, py);
-#pragma unroll
-        for (int i = 0; i < NCP; ++i)  // ... multi-sprite cells are composited by the lanes that hold them ...
-          if (!(hdr[i] & REC_FAST)) compose_row(px[i], s_atlas, s_rec + hdr[i] * R.rec_stride, map, vi.ao, py);
-#pragma unroll
-        for (int i = 0; i < NCP; ++i) {  // ... pack and stage
+        for (int i = 0; i < NCP; ++i) {  // ... then each cell's sprite row: load (a multi-sprite cell loads a dummy), composite, pack, stage
           const int cx = cg + 4 * i;
-          if (cx < R.view_w) store_row(buf + py * prow_bytes + cx * 24, px[i]);
+          uint32_t q[8];
+          fast_row(q, s_atlas, (hdr[i] & REC_FAST) ? hdr[i] : 0, py);
+          if (!(hdr[i] & REC_FAST)) compose_row(q, s_atlas, s_rec + hdr[i] * R.rec_stride, map, vi.ao, py);
+          if (cx < R.view_w) store_row(buf + py * R.prow_bytes + cx * 24, q);
         }
         }
         if (!(flags & 128u)) fence_async_smem();  // make this lane's writes visible to the async (TMA) proxy
         __syncwarp();
-        if (lane == 0 && !(flags & 32u)) bulk_store(S.rgb + ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * pitem_bytes, buf, (uint32_t)pitem_bytes, store_policy);
+        if (lane == 0 && !(flags & 32u)) bulk_store(S.rgb + ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * R.pitem_bytes, buf, (uint32_t)R.pitem_bytes, store_policy);
       } else {
-        const int wi = item - n_player_items, wy = wi >> (3 - wlog);
+        const int wi = item - R.n_player_items, wy = wi >> (3 - wlog);
         const int py = ((wi & ((8 >> wlog) - 1)) << wlog) | (lane & (wrows - 1)), cg = lane >> wlog;
         const int cstep = 32 >> wlog;
         const int16_t* map = s_map + T.P * R.n_total;
         const uint16_t* rowrec = s_rec + wy * T.W * R.rec_stride;
         int hdr[NCW];
-        uint32_t px[NCW][8];
         if (!(flags & 16u)) {
 #pragma unroll
         for (int i = 0; i < NCW; ++i) {
           const int cx = cg + cstep * i;
-          hdr[i] = cx < T.W ? (int)rowrec[cx * R.rec_stride] : h_oov;
-        }
-#pragma unroll
-        for (int i = 0; i < NCW; ++i) fast_row(px[i], s_atlas, (hdr[i] & REC_FAST) ? hdr[i] : 0, py);
-#pragma unroll
-        for (int i = 0; i < NCW; ++i) {
-          const int cx = min(cg + cstep * i, T.W - 1);
-          if (!(hdr[i] & REC_FAST)) compose_row(px[i], s_atlas, rowrec + cx * R.rec_stride, map, 0, py);
+          hdr[i] = cx < T.W ? (int)rowrec[cx * R.rec_stride] : R.h_oov;
         }
 #pragma unroll
         for (int i = 0; i < NCW; ++i) {
           const int cx = cg + cstep * i;
-          if (cx < T.W) store_row(buf + (py & (wrows - 1)) * wrow_bytes + cx * 24, px[i]);
+          uint32_t q[8];
+          fast_row(q, s_atlas, (hdr[i] & REC_FAST) ? hdr[i] : 0, py);
+          if (!(hdr[i] & REC_FAST)) compose_row(q, s_atlas, rowrec + min(cx, T.W - 1) * R.rec_stride, map, 0, py);
+          if (cx < T.W) store_row(buf + (py & (wrows - 1)) * R.wrow_bytes + cx * 24, q);
         }
         }
         if (!(flags & 128u)) fence_async_smem();
         __syncwarp();
-        if (lane == 0 && !(flags & 32u)) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wi * witem_bytes, buf, (uint32_t)witem_bytes, store_policy);
+        if (lane == 0 && !(flags & 32u)) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wi * R.witem_bytes, buf, (uint32_t)R.witem_bytes, store_policy);
       }
     }
     team_sync(team);  // every warp is done with s_rec / s_view
