@@ -121,6 +121,8 @@ enum MpbComp {
                                   ip5 n levels, ip6 level_1 state, ip(7+3l) levelIncrement, ip(8+3l) remove, ip(9+3l) freeze;
                                   dp(2l) sourceReward, dp(2l+1) targetReward */
   MPB_C_TERRITORY_TASTE = 31,  /* ip0 role (0 none, 1 rewarded_per_claim, 2 rewarded_per_claim_only); dp0 rewardAmount, dp1 firstClaimRewardMultiplier */
+  MPB_C_ROLE = 32,             /* inert: the role string only matters to RoleBasedRewardTile */
+  MPB_C_ROLE_BASED_REWARD_TILE = 33, /* inert: the compiler rejects configs in which an avatar's role is rewarded */
   MPB_C_COUNT
 };
 

@@ -23,6 +23,7 @@ from __future__ import annotations
 import copy
 import json
 import os
+import random
 import sys
 import types
 from typing import Any, Dict, List, Mapping, Optional, Sequence
@@ -49,7 +50,8 @@ COMP = dict(StateManager=1, Transform=2, Appearance=3, BeamBlocker=4, Edible=5,
             Animation=20, AdditionalSprites=21, Neighborhoods=22,
             DensityRegrow=23, LocationObserver=24, AllBeamBlocker=25,
             Resource=26, ResourceClaimer=27, RewardIndicator=28, Paintbrush=29,
-            GraduatedSanctionsMarking=30, TerritoryTaste=31)
+            GraduatedSanctionsMarking=30, TerritoryTaste=31, Role=32,
+            RoleBasedRewardTile=33)
 COMP_NI, COMP_ND = 16, 6
 ACTION_FIELDS = {'move': 0, 'turn': 1, 'fireZap': 2, 'fireClean': 3,
                  'fireClaim': 3}
@@ -245,15 +247,26 @@ def _map_rows(ascii_map: str) -> List[str]:
   return rows
 
 
-def _expand_prefab(spec, prefabs, out, x, y):
+def _expand_prefab(spec, prefabs, out, x, y, rng):
+  """prefab_utils.lua:44-72 (_createPrefabsFromSpec): a name, or {'type': 'all' | 'choice', 'list': [...]}.
+
+  The reference draws a 'choice' with the env's own random stream when the env is built, so every
+  env instance gets its own layout. Here the draw happens once per compiled blob with `rng`
+  (policy A.20: all env instances of a batch share the layout); without a build seed it is refused.
+  """
   if isinstance(spec, Mapping):
     if spec['type'] == 'all':
       for p in spec['list']:
-        _expand_prefab(p, prefabs, out, x, y)
+        _expand_prefab(p, prefabs, out, x, y, rng)
+    elif spec['type'] == 'choice':
+      if rng is None:
+        raise NotImplementedError(
+            "charPrefabMap type 'choice' (random choice at build time) needs a build_seed: "
+            'the B200 engine draws the layout once per compiled blob')
+      options = list(spec['list'])
+      _expand_prefab(options[rng.randrange(len(options))], prefabs, out, x, y, rng)
     else:
-      raise NotImplementedError(
-          f"charPrefabMap type {spec['type']!r} (random choice at build time) "
-          'is not supported by the B200 engine')
+      raise NotImplementedError(f"charPrefabMap type {spec['type']!r} is not supported by the B200 engine")
   else:
     if spec not in prefabs:
       raise KeyError(f"Prefab with name '{spec}' not found in prefabs.")
@@ -263,7 +276,7 @@ def _expand_prefab(spec, prefabs, out, x, y):
 class WorldModel:
   """Everything the engines need, as python lists prior to packing."""
 
-  def __init__(self, settings: Mapping[str, Any]):
+  def __init__(self, settings: Mapping[str, Any], build_seed: Optional[int] = None):
     s = _plain(settings)
     sim = s['simulation']
     self.level = s['levelName']
@@ -289,11 +302,14 @@ class WorldModel:
     for go in sim.get('gameObjects', []):
       objs.append((go, 0, 0))
     cpm = {str(k): v for k, v in sim['charPrefabMap'].items()}
+    rng = random.Random(build_seed) if build_seed is not None else None
     for y, row in enumerate(rows):
       for x, ch in enumerate(row):
         if ch in cpm:
-          _expand_prefab(cpm[ch], sim['prefabs'], objs, x, y)
+          _expand_prefab(cpm[ch], sim['prefabs'], objs, x, y, rng)
     self.objects_cfg = objs
+    self.avatar_roles = set()
+    self.rewarded_roles = set()
 
     # ---- layers, hits (base_simulation.lua:263-271; addHits) ---------------
     self.layers = list(BASE_LAYERS)
@@ -514,6 +530,14 @@ class WorldModel:
         ip[9] = int(kw['gameFramesPerAnimationFrame'])
         ip[10] = int(kw['loop'])
         ip[11] = int(kw.get('randomStartFrame', False))
+      elif name == 'Role':
+        # component_library.lua Role: a string the avatar carries; only RoleBasedRewardTile reads it.
+        self.avatar_roles.add(str(kw.get('role', 'none')))
+      elif name == 'RoleBasedRewardTile':
+        # component_library.lua:1098-1136: pays rolesToRewards[role] to an avatar that steps on the
+        # tile. Emitted as an inert component; _check_role_tiles() rejects configs in which some
+        # avatar's role is actually rewarded (not the case for any default-role build).
+        self.rewarded_roles.update(str(k) for k in (kw.get('rolesToRewards') or {}))
       elif name == 'Taste' and self.family == 'territory':
         name = 'TerritoryTaste'
         ip[0] = _TERRITORY_TASTE_ROLES[kw.get('role', 'none')]
@@ -653,6 +677,9 @@ def _avatar_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
         cells.append(y * model.W + x)
     if g in ('spawnPoints', 'insideSpawnPoints'):
       sections['spawn_cells_' + str(gi)] = np.array(cells, np.int32)
+      users = int((av[:, 3] == gi).sum())
+      if len(cells) < users:  # (possible when spawn points come from 'choice' prefabs)
+        raise ValueError(f'{users} avatars start in group {g!r} but the map has only {len(cells)} such cells')
   # Static beam blockers: bit h set if a BeamBlocker for hit h sits on the cell.
   flags = np.zeros(model.H * model.W, np.uint8)
   for oid, ci in _objects_with(model, 'BeamBlocker'):
@@ -938,9 +965,16 @@ def _territory_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
 # Entry points
 # ---------------------------------------------------------------------------
 def compile_settings(settings: Mapping[str, Any],
-                     config: Optional[Any] = None) -> bytes:
-  """lab2d settings (+ optional substrate config for API metadata) -> blob."""
-  model = WorldModel(settings)
+                     config: Optional[Any] = None,
+                     build_seed: Optional[int] = None) -> bytes:
+  """lab2d settings (+ optional substrate config for API metadata) -> blob.
+
+  `build_seed` resolves 'choice' prefabs (see _expand_prefab); configs without them ignore it.
+  """
+  model = WorldModel(settings, build_seed)
+  rewarded = model.avatar_roles & model.rewarded_roles
+  if rewarded:
+    raise NotImplementedError(f'RoleBasedRewardTile paying roles {sorted(rewarded)} is not supported by the B200 engine')
   P = model.num_players
   meta = np.zeros(META_COUNT, np.int32)
   atlas = model.sprites.atlas()
@@ -1020,9 +1054,10 @@ def compile_settings(settings: Mapping[str, Any],
 
 
 def compile_substrate(name: str, roles: Optional[Sequence[str]] = None,
-                      root: Optional[str] = None) -> bytes:
+                      root: Optional[str] = None,
+                      build_seed: Optional[int] = None) -> bytes:
   """Compiles a named reference substrate (needs a reference checkout)."""
   config = load_reference_config(name, root)
   roles = tuple(roles) if roles is not None else tuple(config.default_player_roles)
   settings = config.lab2d_settings_builder(roles=roles, config=config)
-  return compile_settings(settings, config)
+  return compile_settings(settings, config, build_seed)

@@ -478,8 +478,6 @@ int build_plan(mp_engine* E) {
   R.view_w = T.view_l + T.view_r + 1; R.view_h = T.view_f + T.view_b + 1;
   R.player_bytes = R.view_w * R.view_h * 192;
   R.world_bytes = T.H * T.W * 192;
-  R.wstrip_log2 = 2;  // 4 pixel rows per WORLD.RGB strip
-  R.stage_bytes = RENDER_SLOTS * round_up(std::max(R.view_w * 192, T.W * 24 * (1 << R.wstrip_log2)), 128);
   R.grid_bytes = T.L * T.cells_pad * 2;
   R.n_total = E->n_total;
   R.atlas_bytes = R.n_total * 1024;
@@ -490,12 +488,21 @@ int build_plan(mp_engine* E) {
   R.off_pair = off; off += round_up(R.n_total * R.n_total, 128);
   R.off_map = off; off += round_up((T.P + 1) * R.n_total * 2, 128);
   R.off_team0 = off;
-  int toff = 0;
-  R.toff_grid = toff; toff += round_up(R.grid_bytes, 128);
-  R.toff_rec = toff; toff += round_up(T.cells * R.rec_stride * 2, 128);
-  R.toff_stage = toff; toff += (TEAM_THREADS / 32) * R.stage_bytes;
-  R.team_stride = toff;
-  R.smem_bytes = R.off_team0 + RENDER_TEAMS * R.team_stride;
+  // the largest team (most warps in flight) whose staging buffers still fit; WORLD.RGB strips of 4 pixel rows
+  // first, of 2 if that is what it takes
+  R.smem_bytes = 1 << 30;
+  for (int wlog = 2; wlog >= 1 && R.smem_bytes > 227 * 1024; --wlog)
+    for (int tt = TEAM_THREADS; tt >= 128 && R.smem_bytes > 227 * 1024; tt -= 128) {
+      R.wstrip_log2 = wlog;
+      R.team_threads = tt;
+      R.stage_bytes = RENDER_SLOTS * round_up(std::max(R.view_w * 192, T.W * 24 * (1 << wlog)), 128);
+      int toff = 0;
+      R.toff_grid = toff; toff += round_up(R.grid_bytes, 128);
+      R.toff_rec = toff; toff += round_up(T.cells * R.rec_stride * 2, 128);
+      R.toff_stage = toff; toff += (tt / 32) * R.stage_bytes;
+      R.team_stride = toff;
+      R.smem_bytes = R.off_team0 + RENDER_TEAMS * R.team_stride;
+    }
   if (R.smem_bytes > 227 * 1024) return fail(MP_E_UNSUPPORTED, "render kernel needs %d B of shared memory (> 227 KB)", R.smem_bytes);
   return MP_OK;
 }
@@ -520,7 +527,7 @@ int launch_render(mp_engine* E, cudaStream_t st) {
   R.prow_bytes = R.view_w * 24; R.wrow_bytes = T.W * 24;
   R.pitem_bytes = R.prow_bytes * 8; R.witem_bytes = R.wrow_bytes << R.wstrip_log2;
   R.h_oob = 0x8000 | (T.oob_sprite * 4); R.h_oov = 0x8000 | (T.oov_sprite * 4);
-  E->render_fn<<<blocks, RENDER_THREADS, R.smem_bytes, st>>>(E->T, E->S, R, E->flags);
+  E->render_fn<<<blocks, RENDER_TEAMS * R.team_threads, R.smem_bytes, st>>>(E->T, E->S, R, E->flags);
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;
@@ -593,8 +600,9 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
     const int ncp = (E->R.view_w + 3) / 4, ncw = (T.W + (32 >> E->R.wstrip_log2) - 1) / (32 >> E->R.wstrip_log2);
     if (ncp <= 3 && ncw <= 3) E->render_fn = k_render<3, 3>;
     else if (ncp <= 3 && ncw <= 4) E->render_fn = k_render<3, 4>;
-    else if (ncp <= 4 && ncw <= 4) E->render_fn = k_render<4, 4>;
-    else { mp_destroy(E); return fail(MP_E_UNSUPPORTED, "view of %d cells / map of %d cells wide (max 16 / 32)", E->R.view_w, T.W); }
+    else if (ncp <= 3 && ncw <= 5) E->render_fn = k_render<3, 5>;
+    else if (ncp <= 4 && ncw <= 5) E->render_fn = k_render<4, 5>;
+    else { mp_destroy(E); return fail(MP_E_UNSUPPORTED, "view of %d cells / map of %d cells wide (max 16 / 40)", E->R.view_w, T.W); }
   }
   cudaError_t ce = cudaFuncSetAttribute(E->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E->R.smem_bytes);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_clean_up, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));

@@ -8,7 +8,8 @@
 //
 // HBM-bound by design: per env-step it reads the ~11 KB sprite grid and writes
 // P*88*88*3 + H*W*192 bytes of observations. One persistent CTA per SM hosts RENDER_TEAMS
-// independent teams of TEAM_THREADS threads that share one shared-memory copy of the sprite atlas
+// independent teams of up to TEAM_THREADS threads (RenderPlan::team_threads, the most that fit in
+// shared memory next to the atlas) that share one shared-memory copy of the sprite atlas
 // (TMA-bulk-loaded once). Each team renders whole envs:
 //   1. the env's grid arrives by TMA bulk copy behind an mbarrier (prefetched one env ahead);
 //   2. a per-cell pass flattens every cell's layer stack into a short record, folding the opaque
@@ -55,6 +56,7 @@ struct RenderPlan {  // host-computed constants of the tiling
   int wstrip_log2;                      // log2 of the pixel rows per WORLD.RGB strip (1 or 2)
   int stage_bytes;                      // warp-private staging buffer: two slots, each one player cell-row or half a world cell-row
   int smem_bytes;
+  int team_threads;                     // threads per team (multiple of 32, <= TEAM_THREADS): what fits in shared memory
   // per-launch constants (depend on the render flags); kept here so that they are constant-bank operands, not registers
   int n_player_items, n_items;           // strips per env: player cell-rows, then WORLD.RGB strips
   int prow_bytes, wrow_bytes;            // one pixel row of a player image / of WORLD.RGB
@@ -110,7 +112,7 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(TEAM_THREADS) : "memory"); }
+__device__ __forceinline__ void team_sync(int team, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(threads) : "memory"); }
 
 // dst, src: R | G<<8 | B<<16 (| A<<24 for src). Integer "over": (s*a + d*(255-a)) / 255, truncated.
 // Branch free on purpose: a == 255 yields src and a == 0 yields dst exactly, so opaque sprites and
@@ -171,7 +173,7 @@ __device__ __forceinline__ void compose_row(uint32_t px[8], const uint8_t* __res
 template <int LMAX>
 __device__ __forceinline__ void cell_pass(const Tables& T, const RenderPlan& R, const uint16_t* __restrict__ s_grid, uint16_t* __restrict__ s_rec,
                                           const uint8_t* __restrict__ s_flags, const uint8_t* __restrict__ s_pair, int ttid, uint32_t dbg) {
-  for (int c = ttid; c < T.cells; c += TEAM_THREADS) {
+  for (int c = ttid; c < T.cells; c += R.team_threads) {
     uint32_t v[LMAX];
 #pragma unroll
     for (int l = 0; l < LMAX; ++l) v[l] = l < T.L ? s_grid[l * T.cells_pad + c] : 0u;
@@ -254,7 +256,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
   __shared__ int s_next_item[RENDER_TEAMS];
 
   const int tid = threadIdx.x;
-  const int team = tid / TEAM_THREADS, ttid = tid % TEAM_THREADS;
+  int team = 0;
+#pragma unroll
+  for (int k = 1; k < RENDER_TEAMS; ++k) team += tid >= k * R.team_threads;
+  const int ttid = tid - team * R.team_threads;
   const int lane = tid & 31, twarp = ttid >> 5;
   uint8_t* s_team = smem + R.off_team0 + team * R.team_stride;
   uint16_t* s_grid = reinterpret_cast<uint16_t*>(s_team + R.toff_grid);
@@ -279,9 +284,9 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
     mbar_expect_tx(gbar, (uint32_t)R.grid_bytes);
     bulk_load(s_grid, S.grid + (size_t)first * T.L * T.cells_pad, (uint32_t)R.grid_bytes, gbar);
   }
-  for (int i = tid; i < (T.P + 1) * R.n_total; i += RENDER_THREADS) s_map[i] = T.sprite_map[i];
-  for (int i = tid; i < R.n_total; i += RENDER_THREADS) s_opaque[i] = T.sprite_opaque[i];
-  for (int i = tid; i < R.n_total * R.n_total; i += RENDER_THREADS) smem[R.off_pair + i] = T.sprite_pair[i];
+  for (int i = tid; i < (T.P + 1) * R.n_total; i += (int)blockDim.x) s_map[i] = T.sprite_map[i];
+  for (int i = tid; i < R.n_total; i += (int)blockDim.x) s_opaque[i] = T.sprite_opaque[i];
+  for (int i = tid; i < R.n_total * R.n_total; i += (int)blockDim.x) smem[R.off_pair + i] = T.sprite_pair[i];
   __syncthreads();  // tables visible to every warp before the first cell pass
   mbar_wait(&bar[0], 0);
   if (first >= S.B) return;
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
       else if (T.L <= 12) cell_pass<12>(T, R, s_grid, s_rec, s_opaque, s_pair, ttid, flags);
       else cell_pass<MP_MAX_LAYERS>(T, R, s_grid, s_rec, s_opaque, s_pair, ttid, flags);
     }
-    team_sync(team);  // records complete; the grid buffer is free again
+    team_sync(team, R.team_threads);  // records complete; the grid buffer is free again
     const int nb = b + n_streams;
     if (ttid == 0 && nb < S.B) {
       mbar_expect_tx(gbar, (uint32_t)R.grid_bytes);
@@ -395,7 +400,7 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
         if (lane == 0 && !(flags & 32u)) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wi * R.witem_bytes, buf, (uint32_t)R.witem_bytes, store_policy);
       }
     }
-    team_sync(team);  // every warp is done with s_rec / s_view
+    team_sync(team, R.team_threads);  // every warp is done with s_rec / s_view
     if (ttid == 0) s_next_item[team] = 0;
     // (the reset is ordered before the next env's item loop by the team barrier after its cell pass)
   }

@@ -12,7 +12,15 @@ PRECOMPILED = {
     'clean_up': (7,),
     'commons_harvest__open': (7, 16),
     'territory__rooms': (9,),
+    'territory__open': (9,),
+    'territory__inside_out': (5,),
+    'commons_harvest__closed': (7,),
+    'commons_harvest__partnership': (7,),
 }
+
+# Substrates whose maps hold 'choice' prefabs (prefab_utils.lua:63-65): the reference draws them per env
+# instance at build time; a compiled blob fixes one draw (policy A.20), made with this seed.
+BUILD_SEEDS = {'territory__inside_out': 0}
 
 
 def blob_path(name: str, num_players: int) -> str:
@@ -38,7 +46,7 @@ def load_blob(name: str, roles: Optional[Sequence[str]] = None) -> bytes:
     raise FileNotFoundError(
         f'no precompiled blob for {name!r} with roles {roles!r} and no Melting Pot '
         'reference checkout to compile from (set MELTINGPOT_REFERENCE_ROOT)')
-  return compiler.compile_substrate(name, roles)
+  return compiler.compile_substrate(name, roles, build_seed=BUILD_SEEDS.get(name))
 
 
 def _is_default_role(name: str, role: str) -> bool:

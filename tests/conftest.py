@@ -47,3 +47,27 @@ def commons16_blob():
 def territory_blob():
   from meltingpot_b200 import substrates
   return substrates.load_blob('territory__rooms', ('default',) * 9)
+
+
+@pytest.fixture(scope='session')
+def territory_open_blob():
+  from meltingpot_b200 import substrates
+  return substrates.load_blob('territory__open', ('default',) * 9)
+
+
+@pytest.fixture(scope='session')
+def commons_closed_blob():
+  from meltingpot_b200 import substrates
+  return substrates.load_blob('commons_harvest__closed', ('default',) * 7)
+
+
+@pytest.fixture(scope='session')
+def territory_inside_out_blob():
+  from meltingpot_b200 import substrates
+  return substrates.load_blob('territory__inside_out', ('default',) * 5)
+
+
+@pytest.fixture(scope='session')
+def commons_partnership_blob():
+  from meltingpot_b200 import substrates
+  return substrates.load_blob('commons_harvest__partnership', ('default',) * 7)

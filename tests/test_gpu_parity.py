@@ -140,3 +140,27 @@ def _zap_heavy(t, B, P, A, rng):
 def test_territory_rooms_zap_heavy(territory_blob, oracle):
   stats = parity.compare_rollout(territory_blob, oracle, num_envs=12, steps=500, seed=17, actions_fn=_zap_heavy, pixels_every=5)
   assert stats['zaps'] > 20
+
+
+def test_territory_open_random_rollout(territory_open_blob, oracle):
+  # BOUNDED 39x23 map (wider than 32 cells: 5 cells per lane per WORLD.RGB strip).
+  stats = parity.compare_rollout(territory_open_blob, oracle, num_envs=12, steps=500, seed=6, pixels_every=3)
+  assert stats['rewards'] > 50
+
+
+def test_commons_harvest_closed_random_rollout(commons_closed_blob, oracle):
+  # same components as commons_harvest__open on a walled map.
+  stats = parity.compare_rollout(commons_closed_blob, oracle, num_envs=16, steps=500, seed=8, pixels_every=3)
+  assert stats['eaten'] > 20
+
+
+def test_territory_inside_out_random_rollout(territory_inside_out_blob, oracle):
+  # 5 players; the map's 'choice' prefabs are drawn once per blob (policy A.20).
+  stats = parity.compare_rollout(territory_inside_out_blob, oracle, num_envs=12, steps=500, seed=12, pixels_every=3)
+  assert stats['rewards'] > 50
+
+
+def test_commons_harvest_partnership_random_rollout(commons_partnership_blob, oracle):
+  # adds the (inert for default roles) Role / RoleBasedRewardTile components.
+  stats = parity.compare_rollout(commons_partnership_blob, oracle, num_envs=16, steps=500, seed=14, pixels_every=3)
+  assert stats['eaten'] > 20

@@ -22,7 +22,7 @@ def main(argv):
     roles = tuple(config.default_player_roles)
     if players:
       roles = (roles[0],) * int(players)
-    blob = compiler.compile_substrate(name, roles)
+    blob = compiler.compile_substrate(name, roles, build_seed=substrates.BUILD_SEEDS.get(name))
     path = substrates.blob_path(name, len(roles))
     with open(path, 'wb') as f:
       f.write(blob)
