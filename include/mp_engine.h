@@ -36,7 +36,14 @@ enum {
 enum {
   MP_FLAG_RENDER_WORLD = 1u << 0, /* produce WORLD.RGB (base_simulation.lua:347-362) */
   MP_FLAG_RENDER_PLAYERS = 1u << 1, /* produce {i}.RGB (avatar_library.lua:264-276) */
-  MP_FLAG_DEFAULT = 3u
+  MP_FLAG_DEFAULT = 3u,
+  /* Diagnostics for tools/render_ceiling.py (the images are wrong or absent while any is set):
+   * time the renderer's store path and its compositing separately. */
+  MP_FLAG_DEBUG_NO_COMPOSE = 1u << 4,   /* issue the stores without drawing */
+  MP_FLAG_DEBUG_NO_STORE = 1u << 5,     /* draw without storing */
+  MP_FLAG_DEBUG_REUSE_RECORDS = 1u << 6, /* per-cell pass only for the first env of each team */
+  MP_FLAG_DEBUG_NO_FENCE = 1u << 7,     /* skip the generic->async proxy fence */
+  MP_FLAG_DEBUG_TOP_SPRITE_ONLY = 1u << 8 /* every cell drawn as its top sprite */
 };
 
 /* Device buffers owned by the engine; valid until mp_destroy. Contents are overwritten by the
@@ -109,6 +116,15 @@ int mp_launch_count(mp_handle h, uint64_t* out);
 
 /* Algorithmic bytes one env-step moves (SURVEY.md section 8d formula), for roofline reports. */
 int mp_algorithmic_bytes(mp_handle h, uint64_t* per_env_step, uint64_t* render_per_env_step);
+
+/* Snapshot / restore of every env instance. The reference has no counterpart
+ * (a dmlab2d env cannot be cloned); here the state is a handful of SoA arrays and the random numbers are
+ * addressed by (seed, env, frame), so a byte copy is a complete checkpoint. A snapshot is an opaque string of
+ * mp_state_size() bytes in host memory, valid for an engine created from the same blob with the same num_envs,
+ * seed and env_index_base. mp_state_load re-renders the observations; both calls synchronise `stream`. */
+int mp_state_size(mp_handle h, uint64_t* bytes);
+int mp_state_save(mp_handle h, void* host_dst, void* stream);
+int mp_state_load(mp_handle h, const void* host_src, void* stream);
 
 /* Diagnostic: the renderer's sprite tables. *n_total = atlas sprites including the pre-merged ones;
  * pair[n_total * n_total] = pre-merged sprite for (bottom, top) or 0; flags[n_total] bit 0 opaque,

@@ -103,6 +103,8 @@ struct mp_engine {
   void (*render_fn)(Tables, State, RenderPlan, uint32_t) = nullptr;
   uint64_t algo_bytes = 0, render_bytes = 0;
   std::vector<uint8_t> host_pair, host_sflags;  // kept for mp_debug_render_tables
+  std::vector<std::pair<void*, size_t>> state_spans;  // what mp_state_save / mp_state_load copy
+  uint64_t state_bytes = 0;
 
   template <typename T>
   int upload(const std::vector<T>& host, const T** out) {
@@ -488,11 +490,11 @@ int build_plan(mp_engine* E) {
   R.off_pair = off; off += round_up(R.n_total * R.n_total, 128);
   R.off_map = off; off += round_up((T.P + 1) * R.n_total * 2, 128);
   R.off_team0 = off;
-  // the largest team (most warps in flight) whose staging buffers still fit; WORLD.RGB strips of 4 pixel rows
-  // first, of 2 if that is what it takes
+  // the largest team (most warps in flight) whose staging buffers still fit, with WORLD.RGB strips of 4 pixel
+  // rows if possible and of 2 otherwise
   R.smem_bytes = 1 << 30;
-  for (int wlog = 2; wlog >= 1 && R.smem_bytes > 227 * 1024; --wlog)
-    for (int tt = TEAM_THREADS; tt >= 128 && R.smem_bytes > 227 * 1024; tt -= 128) {
+  for (int tt = TEAM_THREADS; tt >= 128 && R.smem_bytes > 227 * 1024; tt -= 128)
+    for (int wlog = 2; wlog >= 1 && R.smem_bytes > 227 * 1024; --wlog) {
       R.wstrip_log2 = wlog;
       R.team_threads = tt;
       R.stage_bytes = RENDER_SLOTS * round_up(std::max(R.view_w * 192, T.W * 24 * (1 << wlog)), 128);
@@ -587,6 +589,18 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
       (rc = E->alloc(B * P, &E->d_actions))) {
     mp_destroy(E);
     return rc;
+  }
+  {  // everything a later step depends on, plus the current timestep scalars; the images are re-rendered on load
+    const size_t ns = std::max<size_t>(1, T.n_scalar);
+    auto span = [&](void* p, size_t bytes) { E->state_spans.push_back({p, bytes}); E->state_bytes += bytes; };
+    span(S.grid, B * T.L * T.cells_pad * sizeof(*S.grid)); span(S.avatar, B * P * 4 * sizeof(*S.avatar));
+    span(S.av_timer, B * P * 4 * sizeof(*S.av_timer)); span(S.apple, B * T.nA_pad * sizeof(*S.apple));
+    span(S.dirt, B * T.nD_pad * sizeof(*S.dirt)); span(S.water, B * T.nW_pad * sizeof(*S.water));
+    span(S.apple_count, B * T.nA_pad * sizeof(*S.apple_count)); span(S.fam_u8, B * (size_t)S.fam_u8_stride * sizeof(*S.fam_u8));
+    span(S.fam_u16, B * (size_t)S.fam_u16_stride * sizeof(*S.fam_u16)); span(S.av_extra, B * P * 8 * sizeof(*S.av_extra));
+    span(S.packed, B * (P + 2) * sizeof(*S.packed)); span(S.env, B * ENV_COLS * sizeof(*S.env));
+    span(S.reward, B * P * sizeof(*S.reward)); span(S.discount, B * sizeof(*S.discount));
+    span(S.step_type, B * sizeof(*S.step_type)); span(S.scalar_obs, ns * B * P * sizeof(*S.scalar_obs));
   }
   // episode counter starts at -1 so that the first reset plays episode 0; envs start "done".
   {
@@ -689,6 +703,52 @@ int mp_reset_host(mp_handle h, const mp_host_outputs* out, void* stream) {
   int rc = launch_state(h, nullptr, nullptr, 1, st);
   if (!rc) rc = launch_render(h, st);
   if (!rc) rc = copy_out(h, out, st);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return MP_OK;
+}
+
+namespace {
+struct SnapshotHeader { char magic[4]; uint32_t version; uint64_t num_envs, payload_bytes, n_spans; };
+}
+
+int mp_state_size(mp_handle h, uint64_t* bytes) {
+  if (!h || !bytes) return fail(MP_E_INVALID, "mp_state_size: null argument");
+  *bytes = sizeof(SnapshotHeader) + h->state_bytes;
+  return MP_OK;
+}
+
+int mp_state_save(mp_handle h, void* host_dst, void* stream) {
+  if (!h || !host_dst) return fail(MP_E_INVALID, "mp_state_save: null argument");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  SnapshotHeader hd{{'M', 'P', 'S', '1'}, 1u, (uint64_t)h->B, h->state_bytes, (uint64_t)h->state_spans.size()};
+  memcpy(host_dst, &hd, sizeof(hd));
+  uint8_t* dst = static_cast<uint8_t*>(host_dst) + sizeof(hd);
+  for (const auto& sp : h->state_spans) {
+    CUDA_TRY(cudaMemcpyAsync(dst, sp.first, sp.second, cudaMemcpyDeviceToHost, st));
+    dst += sp.second;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return MP_OK;
+}
+
+int mp_state_load(mp_handle h, const void* host_src, void* stream) {
+  if (!h || !host_src) return fail(MP_E_INVALID, "mp_state_load: null argument");
+  SnapshotHeader hd;
+  memcpy(&hd, host_src, sizeof(hd));
+  if (memcmp(hd.magic, "MPS1", 4) != 0 || hd.version != 1u) return fail(MP_E_INVALID, "mp_state_load: not a snapshot");
+  if (hd.num_envs != (uint64_t)h->B || hd.payload_bytes != h->state_bytes || hd.n_spans != h->state_spans.size())
+    return fail(MP_E_INVALID, "mp_state_load: snapshot of %llu envs / %llu bytes does not fit this engine (%d envs / %llu bytes)",
+                (unsigned long long)hd.num_envs, (unsigned long long)hd.payload_bytes, h->B, (unsigned long long)h->state_bytes);
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint8_t* src = static_cast<const uint8_t*>(host_src) + sizeof(hd);
+  for (const auto& sp : h->state_spans) {
+    CUDA_TRY(cudaMemcpyAsync(sp.first, src, sp.second, cudaMemcpyHostToDevice, st));
+    src += sp.second;
+  }
+  int rc = launch_render(h, st);
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(st));
   return MP_OK;

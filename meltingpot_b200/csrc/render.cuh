@@ -97,14 +97,9 @@ __device__ __forceinline__ uint64_t make_evict_first_policy() {
   return policy;
 }
 __device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes, uint64_t policy) {
-#ifdef MP_NO_STORE_HINT
-  (void)policy;
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-#else
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
                "r"(bytes), "l"(policy)
                : "memory");
-#endif
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 template <int N>
@@ -210,13 +205,6 @@ __device__ __forceinline__ void cell_pass(const Tables& T, const RenderPlan& R, 
   }
 }
 
-__device__ __forceinline__ void fixed_row(uint32_t px[8], const uint8_t* __restrict__ s_atlas, int sprite, int py) {
-  const uint8_t* t = s_atlas + (sprite * 4) * 256 + py * 16;
-  const uint4 lo = *reinterpret_cast<const uint4*>(t);
-  const uint4 hi = *reinterpret_cast<const uint4*>(t + 128);
-  px[0] = lo.x; px[1] = lo.y; px[2] = lo.z; px[3] = lo.w; px[4] = hi.x; px[5] = hi.y; px[6] = hi.z; px[7] = hi.w;
-}
-
 // 8 RGBA pixels -> 24 packed RGB bytes at `dst` (8-byte aligned).
 __device__ __forceinline__ void store_row(uint8_t* dst, const uint32_t px[8]) {
   uint2 a, b, c;
@@ -320,20 +308,12 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
     }
 
     // ---- strip items, pulled by warps -------------------------------------------------------------
-#ifndef MP_V_NOPREFETCH
     int next_item = 0;  // claimed one strip ahead so that the atomic's latency hides behind the strip being drawn
     if (lane == 0) next_item = atomicAdd(&s_next_item[team], 1);
     for (;;) {
       const int item = __shfl_sync(MP_FULL, next_item, 0);
       if (item >= R.n_items) break;
       if (lane == 0) next_item = atomicAdd(&s_next_item[team], 1);
-#else
-    for (;;) {
-      int item = 0;
-      if (lane == 0) item = atomicAdd(&s_next_item[team], 1);
-      item = __shfl_sync(MP_FULL, item, 0);
-      if (item >= R.n_items) break;
-#endif
       uint8_t* buf = s_stage + (slot % RENDER_SLOTS) * slot_bytes;
       ++slot;
       if (lane == 0) bulk_wait_read<RENDER_SLOTS - 1>();  // the store that last used this slot has drained

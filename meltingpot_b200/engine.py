@@ -23,7 +23,7 @@ MP_FLAG_DEFAULT = 3
 EXPORTED_SYMBOLS = (
     'mp_create', 'mp_destroy', 'mp_set_flags', 'mp_reset', 'mp_step',
     'mp_step_state', 'mp_render', 'mp_get_buffers', 'mp_step_host',
-    'mp_reset_host', 'mp_launch_count', 'mp_algorithmic_bytes', 'mp_debug_render_tables',
+    'mp_reset_host', 'mp_launch_count', 'mp_algorithmic_bytes', 'mp_debug_render_tables', 'mp_state_size', 'mp_state_save', 'mp_state_load',
     'mp_last_error', 'mp_version',
 )
 
@@ -81,6 +81,9 @@ def load_library() -> ctypes.CDLL:
   lib.mp_launch_count.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
   lib.mp_algorithmic_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64),
                                        ctypes.POINTER(ctypes.c_uint64)]
+  lib.mp_state_size.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
+  lib.mp_state_save.argtypes = [vp, vp, vp]
+  lib.mp_state_load.argtypes = [vp, vp, vp]
   lib.mp_debug_render_tables.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), vp, vp]
   lib.mp_last_error.restype = ctypes.c_char_p
   lib.mp_version.restype = ctypes.c_char_p
@@ -245,6 +248,18 @@ class Engine:
     n = ctypes.c_uint64(0)
     _check(self._lib.mp_launch_count(self._h, ctypes.byref(n)))
     return int(n.value)
+
+  def save_state(self, stream=None) -> bytes:
+    """Snapshot of every env instance (mp_state_save); restore with load_state on an identically built engine."""
+    n = ctypes.c_uint64(0)
+    _check(self._lib.mp_state_size(self._h, ctypes.byref(n)))
+    buf = ctypes.create_string_buffer(n.value)
+    _check(self._lib.mp_state_save(self._h, buf, self._stream(stream)))
+    return buf.raw
+
+  def load_state(self, snapshot: bytes, stream=None) -> None:
+    buf = ctypes.create_string_buffer(snapshot, len(snapshot))
+    _check(self._lib.mp_state_load(self._h, buf, self._stream(stream)))
 
   def render_tables(self):
     """(pair[n, n], flags[n]) uint8 numpy arrays of the renderer's sprite tables (diagnostic)."""

@@ -173,6 +173,15 @@ class BatchedSubstrate:
     self._engine.step(actions.contiguous())
     return self._timestep()
 
+  def save_state(self) -> bytes:
+    """Snapshot of every env instance (no reference counterpart)."""
+    return self._engine.save_state()
+
+  def load_state(self, snapshot: bytes) -> BatchedTimeStep:
+    """Restores a snapshot taken from an identically built BatchedSubstrate; returns the timestep it held."""
+    self._engine.load_state(snapshot)
+    return self._timestep()
+
   def action_spec(self):
     return tuple(specs_lib.action(self.num_actions) for _ in range(self.num_players))
 

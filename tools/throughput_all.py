@@ -14,6 +14,10 @@ CONFIGS = [
     ('commons_harvest__open', 7, 4096),
     ('territory__rooms', 9, 2048),
     ('territory__rooms', 9, 4096),
+    ('territory__open', 9, 2048),
+    ('territory__inside_out', 5, 4096),
+    ('commons_harvest__closed', 7, 4096),
+    ('commons_harvest__partnership', 7, 4096),
 ]
 PEAK = 6561.6
 if os.path.exists('MEASURED_PEAKS.json'):
