@@ -586,6 +586,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
       (rc = E->alloc(B * ENV_COLS, &S.env)) || (rc = E->alloc(B * P, &S.reward)) || (rc = E->alloc(B, &S.discount)) ||
       (rc = E->alloc(B, &S.step_type)) || (rc = E->alloc(std::max<size_t>(1, T.n_scalar) * B * P, &S.scalar_obs)) ||
       (rc = E->alloc(B * P * E->R.player_bytes, &S.rgb)) || (rc = E->alloc(B * (size_t)E->R.world_bytes, &S.world_rgb)) ||
+      (rc = E->alloc(B * MP_MAX_EVENTS * 3, &S.events)) || (rc = E->alloc(B, &S.n_events)) ||
       (rc = E->alloc(B * P, &E->d_actions))) {
     mp_destroy(E);
     return rc;
@@ -601,6 +602,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
     span(S.packed, B * (P + 2) * sizeof(*S.packed)); span(S.env, B * ENV_COLS * sizeof(*S.env));
     span(S.reward, B * P * sizeof(*S.reward)); span(S.discount, B * sizeof(*S.discount));
     span(S.step_type, B * sizeof(*S.step_type)); span(S.scalar_obs, ns * B * P * sizeof(*S.scalar_obs));
+    span(S.events, B * MP_MAX_EVENTS * 3 * sizeof(*S.events)); span(S.n_events, B * sizeof(*S.n_events));
   }
   // episode counter starts at -1 so that the first reset plays episode 0; envs start "done".
   {
@@ -629,6 +631,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   bf.rgb = S.rgb; bf.world_rgb = S.world_rgb; bf.reward = S.reward; bf.discount = S.discount; bf.step_type = S.step_type;
   bf.scalar_obs = S.scalar_obs; bf.avatar_state = S.avatar; bf.grid = S.grid; bf.timestep_packed = S.packed;
   bf.grid_layers = T.L; bf.grid_cells = T.cells; bf.grid_cells_padded = T.cells_pad;
+  bf.events = S.events; bf.event_count = S.n_events; bf.max_events = MP_MAX_EVENTS;
   // observations + scalars + actions + one read and one write of the compact grid.
   E->render_bytes = (uint64_t)P * E->R.player_bytes + (uint64_t)E->R.world_bytes + (uint64_t)T.L * T.cells * 2;
   E->algo_bytes = (uint64_t)P * E->R.player_bytes + (uint64_t)E->R.world_bytes + 8ull * ((1 + T.n_scalar) * P + 2) + 8ull * P + 2ull * T.L * T.cells * 2;

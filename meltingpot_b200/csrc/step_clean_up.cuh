@@ -252,7 +252,7 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
     while (m) {  // in apple (object) order
       int src = __ffs(m) - 1; m &= m - 1;
       int e = __shfl_sync(MP_FULL, eater, src);
-      if (lane == e) reward += T.eat_reward;
+      if (lane == e) { reward += T.eat_reward; emit_event(S, b, EV_EDIBLE_CONSUMED, e + 1, 0); }
       ate_now |= 1u << e;
     }
   }
@@ -283,7 +283,7 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
       __syncwarp();
       if (ate && lane == 0) sc.apple[ai] |= 2;
     }
-    if (lane == src) { x = sx; y = sy; orient = so; if (ate) reward += T.eat_reward; }
+    if (lane == src) { x = sx; y = sy; orient = so; if (ate) { reward += T.eat_reward; emit_event(S, b, EV_EDIBLE_CONSUMED, src + 1, 0); } }
     if (ate) ate_now |= 1u << src;
     __syncwarp();
   }
@@ -325,12 +325,12 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
           int c = __ffs(hm) - 1; hm &= hm - 1;
           int t = __shfl_sync(MP_FULL, hit_avatar, c);
           if (lane == t) reward += T.zap_penalty;   // zapped avatar is still alive in this round
-          if (lane == src) reward += T.zap_reward;
+          if (lane == src) { reward += T.zap_reward; emit_event(S, b, EV_ZAP, src + 1, t + 1); }
           if (T.zap_remove) zapped |= 1u << t;
         }
       } else {
         bool cleaned = vis && hit_dirt >= 0;
-        if (cleaned) sc.dirt[hit_dirt] |= 2;
+        if (cleaned) { sc.dirt[hit_dirt] |= 2; emit_event(S, b, EV_PLAYER_CLEANED, src + 1, 0); }
         if (__any_sync(MP_FULL, cleaned)) cleaned_now |= 1u << src;  // Cleaner:setCumulant
       }
       if (vis && !blocked && cell >= 0) {
@@ -363,7 +363,7 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
     if (ate && lane == 0) sc.apple[ai] |= 2;
     if (lane == src) {
       x = target % T.W; y = target / T.W; orient = (int)(w.z & 3u); alive = 1; state_frame = n;
-      if (ate) reward += T.eat_reward;
+      if (ate) { reward += T.eat_reward; emit_event(S, b, EV_EDIBLE_CONSUMED, src + 1, 0); }
     }
     if (ate) ate_now |= 1u << src;
     __syncwarp();
@@ -441,8 +441,11 @@ __global__ void __launch_bounds__(128) k_step_clean_up(Tables T, State S, const 
   const int b = blockIdx.x * 4 + warp;
   if (b >= S.B) return;
   WarpScratch sc = carve_scratch(T, smem + warp * warp_scratch_bytes(T));
+  if (mode == 1 && !(mask == nullptr || mask[b])) return;
+  if (lane == 0) S.n_events[b] = 0;
+  __syncwarp();
   if (mode == 1) {
-    if (mask == nullptr || mask[b]) clean_up_reset(T, S, b, lane, sc);
+    clean_up_reset(T, S, b, lane, sc);
     return;
   }
   if (S.env[(size_t)b * ENV_COLS + ENV_DONE]) clean_up_reset(T, S, b, lane, sc);

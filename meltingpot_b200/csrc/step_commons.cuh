@@ -190,7 +190,7 @@ __device__ void commons_step(const Tables& T, const State& S, int b, int lane, c
         ++n_events;
       }
     }
-    if (lane == src) { x = sx; y = sy; orient = so; if (ate) reward += T.eat_reward; }
+    if (lane == src) { x = sx; y = sy; orient = so; if (ate) { reward += T.eat_reward; emit_event(S, b, EV_EDIBLE_CONSUMED, src + 1, 0); } }
     __syncwarp();
   }
   // zap beams
@@ -221,7 +221,7 @@ __device__ void commons_step(const Tables& T, const State& S, int b, int lane, c
       int c = __ffs(hm) - 1; hm &= hm - 1;
       int t = __shfl_sync(MP_FULL, hit_avatar, c);
       if (lane == t) reward += T.zap_penalty;
-      if (lane == src) reward += T.zap_reward;
+      if (lane == src) { reward += T.zap_reward; emit_event(S, b, EV_ZAP, src + 1, t + 1); }
       if (T.zap_remove) zapped |= 1u << t;
     }
     if (vis && !blocked && cell >= 0) {
@@ -251,7 +251,7 @@ __device__ void commons_step(const Tables& T, const State& S, int b, int lane, c
     if (fresh) ++n_events;
     if (lane == src) {
       x = target % T.W; y = target / T.W; orient = (int)(w.z & 3u); alive = 1; state_frame = n;
-      if (ate) reward += T.eat_reward;
+      if (ate) { reward += T.eat_reward; emit_event(S, b, EV_EDIBLE_CONSUMED, src + 1, 0); }
     }
     __syncwarp();
   }
@@ -271,7 +271,7 @@ __device__ void commons_step(const Tables& T, const State& S, int b, int lane, c
       const int cell = T.ch_apple[i * 4 + 1];
       const int o = sc.occ[cell];
       if (o >= 1 && o <= T.P) {  // an avatar stands here: eaten at once
-        if (lane == o - 1) reward += T.eat_reward;
+        if (lane == o - 1) { reward += T.eat_reward; emit_event(S, b, EV_EDIBLE_CONSUMED, o, 0); }
         __syncwarp();
         if (lane == 0) { s_state[i] |= 64; s_events[n_events] = (int16_t)i; }
         ++n_events;
@@ -343,8 +343,11 @@ __global__ void __launch_bounds__(128) k_step_commons(Tables T, State S, const i
   const int b = blockIdx.x * 4 + warp;
   if (b >= S.B) return;
   WarpScratch sc = carve_scratch(T, smem + warp * warp_scratch_bytes(T));
+  if (mode == 1 && !(mask == nullptr || mask[b])) return;
+  if (lane == 0) S.n_events[b] = 0;
+  __syncwarp();
   if (mode == 1) {
-    if (mask == nullptr || mask[b]) commons_reset(T, S, b, lane, sc);
+    commons_reset(T, S, b, lane, sc);
     return;
   }
   if (S.env[(size_t)b * ENV_COLS + ENV_DONE]) commons_reset(T, S, b, lane, sc);

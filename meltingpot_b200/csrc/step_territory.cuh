@@ -316,13 +316,14 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
                 sc.r2_state[rr] = 1; sc.r2_changed[rr] = 1;
                 sc.r[RU_FLAGS][rr] = (sc.r[RU_FLAGS][rr] & ~RF_ACTIVE) | RF_DESTROYED;
                 sc.r[RU_TEX][rr] = 1; sc.r[RU_DMG][rr] = 0;  // texture 'destroyed', damage indicator 'inactive' (round 2)
+                emit_event(S, b, EV_DESTROYED_RESOURCE, src + 1, 0);
               }
               sc.r[RU_HEALTH][rr] = (uint8_t)h;
             }
           } else {
             // Zapper:onHit (avatar_library.lua:652-681), then the marking on the same cell (:1049-1093)
             if (lane == t) reward += T.zap_penalty;
-            if (lane == src) reward += T.zap_reward;
+            if (lane == src) { reward += T.zap_reward; emit_event(S, b, EV_ZAP, src + 1, t + 1); }
             const int t_mk = __shfl_sync(MP_FULL, mk_on, t), t_level = __shfl_sync(MP_FULL, level, t);
             if (t_mk && t_level >= 1 && t_level <= T.mark_n_levels) {
               const int l = t_level - 1;
@@ -330,12 +331,13 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
               if (lane == t) {
                 reward += T.mark_tgt_reward[l];
                 level += T.mark_inc[l];
-                if (T.mark_remove[l]) { removal = 1; move_ok = 0; freeze = 1; nozap = 1; nozap_cnt = 1; }
+                if (T.mark_remove[l]) { removal = 1; move_ok = 0; freeze = 1; nozap = 1; nozap_cnt = 1; emit_event(S, b, EV_REMOVAL, src + 1, t + 1); }
                 else {
                   shown = level;  // _setLevel (round 2)
                   if (T.mark_freeze[l] > 0) { move_ok = 0; freeze = T.mark_freeze[l]; nozap = 1; nozap_cnt = T.mark_freeze[l]; }
                 }
                 mark_t = 0;
+                emit_event(S, b, EV_SANCTIONING, src + 1, t + 1);
               }
             }
           }
@@ -348,6 +350,7 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
         if (sc.r[RU_STATE][res] != 2 + src && !(flags_r & RF_DESTROYED)) {
           if (sc.r2_state[res] != 2 + src) { sc.r2_state[res] = (uint8_t)(2 + src); sc.r2_changed[res] = 1; }
           sc.r[RU_FLAGS][res] = flags_r & ~(RF_ACTIVE | RF_NEVER_CLAIMED);
+          emit_event(S, b, EV_CLAIMED_RESOURCE, src + 1, 0);
         }
       }
       if (vis && !blocked && cell >= 0) {
@@ -427,6 +430,8 @@ __global__ void __launch_bounds__(128) k_step_territory(Tables T, State S, const
   const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
   const bool reset = mode == 1 ? (mask == nullptr || mask[b]) : (env[ENV_DONE] != 0);
   if (mode == 1 && !reset) return;
+  if (lane == 0) S.n_events[b] = 0;
+  __syncwarp();
   if (reset) {
     const int episode = env[ENV_EPISODE] + 1;
     __syncwarp();

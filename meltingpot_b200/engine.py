@@ -41,6 +41,7 @@ class MpBuffers(ctypes.Structure):
       ('grid_layers', ctypes.c_int32), ('grid_cells', ctypes.c_int32),
       ('grid_cells_padded', ctypes.c_int32),
       ('timestep_packed', ctypes.c_void_p),
+      ('events', ctypes.c_void_p), ('event_count', ctypes.c_void_p), ('max_events', ctypes.c_int32),
   ]
 
 
@@ -89,6 +90,13 @@ def load_library() -> ctypes.CDLL:
   lib.mp_version.restype = ctypes.c_char_p
   _lib = lib
   return lib
+
+
+EVENT_NAMES = {1: 'zap', 2: 'edible_consumed', 3: 'player_cleaned', 4: 'claimed_resource',
+               5: 'destroyed_resource', 6: 'sanctioning', 7: 'removal_due_to_sanctioning'}
+# argument names of each event's dict payload (second one unused for single-argument events)
+EVENT_FIELDS = {1: ('source', 'target'), 2: ('player_index',), 3: ('player_index',), 4: ('player_index',),
+                5: ('player_index',), 6: ('source', 'target'), 7: ('source', 'target')}
 
 
 class EngineError(RuntimeError):
@@ -157,6 +165,8 @@ class Engine:
     self.avatar_state = view(bufs.avatar_state, (B, P, 4), '<i4', torch.int32)
     self.grid = view(bufs.grid, (B, bufs.grid_layers, bufs.grid_cells_padded), '<i2', torch.int16)
     self.timestep_packed = view(bufs.timestep_packed, (B, P + 2), '<f8', torch.float64)
+    self.events = view(bufs.events, (B, bufs.max_events, 3), '<i4', torch.int32)
+    self.event_count = view(bufs.event_count, (B,), '<i4', torch.int32)
 
   # -- lifecycle -----------------------------------------------------------------
   def close(self) -> None:

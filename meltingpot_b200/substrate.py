@@ -173,6 +173,10 @@ class BatchedSubstrate:
     self._engine.step(actions.contiguous())
     return self._timestep()
 
+  def events(self):
+    """(event_count int32 [B], events int32 [B, max_events, 3]) of the last step; rows are (type, a, b), unordered."""
+    return self._engine.event_count, self._engine.events
+
   def save_state(self) -> bytes:
     """Snapshot of every env instance (no reference counterpart)."""
     return self._engine.save_state()
@@ -266,8 +270,23 @@ class Substrate(dm_env.Environment):
     return self._last_observation
 
   def events(self) -> Sequence[tuple]:
-    """Engine events ('zap', 'edible_consumed', ...) are not exported by the CUDA engine yet."""
-    return []
+    """Events of the last reset/step in dmlab2d's shape: (name, [b'dict', b'key', array(value), ...]).
+
+    Covers the events:add calls on the hot path (include/mp_engine.h, mp_buffers.events). dmlab2d's own
+    order within a step is engine-defined and unpinned; here they are sorted by (type, arguments).
+    """
+    from meltingpot_b200 import engine as engine_lib  # pylint: disable=g-import-not-at-top
+    eng = self._batched.engine
+    self._torch.cuda.synchronize(eng.device)
+    n = min(int(eng.event_count[0].item()), int(eng.events.shape[1]))
+    rows = sorted(tuple(int(v) for v in row) for row in eng.events[0, :n].cpu().numpy())
+    out = []
+    for kind, a, b in rows:
+      payload = [b'dict']
+      for key, value in zip(engine_lib.EVENT_FIELDS[kind], (a, b)):
+        payload += [key.encode(), np.array(float(value))]
+      out.append((engine_lib.EVENT_NAMES[kind], payload))
+    return out
 
   def action_spec(self) -> Sequence['dm_env.specs.DiscreteArray']:
     return tuple(self._config.action_spec for _ in range(self._num_players))

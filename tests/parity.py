@@ -15,13 +15,15 @@ def compare_rollout(blob, oracle, num_envs, steps, seed, check_envs=None, action
   eng.reset()
   for e in envs.values():
     e.reset()
-  stats = dict(rewards=0.0, lasts=0, zaps=0, cleaned=0, eaten=0)
+  stats = dict(rewards=0.0, lasts=0, zaps=0, cleaned=0, eaten=0, events=0)
+  code_of = {v: k for k, v in oracle.EVENT_NAMES.items()}
 
   def check(t, acts):
     torch.cuda.synchronize()
     rew = eng.reward.cpu().numpy(); disc = eng.discount.cpu().numpy(); st = eng.step_type.cpu().numpy()
     sc = eng.scalar_obs.cpu().numpy(); av = eng.avatar_state.cpu().numpy()
     grid = eng.grid.cpu().numpy().view(np.uint16)
+    nev = eng.event_count.cpu().numpy(); evs = eng.events.cpu().numpy()
     do_px = (t % pixels_every) == 0
     if do_px:
       idx = torch.as_tensor(check_envs, device='cuda')
@@ -45,6 +47,12 @@ def compare_rollout(blob, oracle, num_envs, steps, seed, check_envs=None, action
         np.testing.assert_array_equal(e.world_rgb(), world[i], err_msg=f'WORLD.RGB {where}')
       stats['rewards'] += float(rew[b].sum())
       stats['lasts'] += int(st[b] == 2)
+      want = sorted((code_of[name], a, b2) for name, a, b2 in e.events())
+      assert nev[b] == len(want), f'event count {where}: oracle {len(want)} gpu {nev[b]}'
+      got = sorted(tuple(int(v) for v in row) for row in evs[b][:min(int(nev[b]), evs.shape[1])])
+      if len(want) <= evs.shape[1]:  # (beyond max_events the engine keeps an unspecified subset)
+        assert got == want, f'events {where}: oracle {want} gpu {got}'
+      stats['events'] += len(want)
       for name, _, _ in e.events():
         key = {'zap': 'zaps', 'player_cleaned': 'cleaned', 'edible_consumed': 'eaten'}.get(name)
         if key:

@@ -164,3 +164,22 @@ def test_commons_harvest_partnership_random_rollout(commons_partnership_blob, or
   # adds the (inert for default roles) Role / RoleBasedRewardTile components.
   stats = parity.compare_rollout(commons_partnership_blob, oracle, num_envs=16, steps=500, seed=14, pixels_every=3)
   assert stats['eaten'] > 20
+
+
+def test_events_reach_the_dm_env_api(clean_up_blob):
+  # substrate.events() / observables().events carry the hot path's events:add calls.
+  from meltingpot_b200 import substrate
+  seen = []
+  with substrate.build('clean_up', roles=('default',) * 7, env_seed=4) as env:
+    env.observables().events.subscribe(seen.append)
+    env.reset()
+    rng = np.random.default_rng(0)
+    names = set()
+    for _ in range(400):
+      env.step(rng.integers(0, 9, 7))
+      for name, payload in env.events():
+        names.add(name)
+        assert payload[0] == b'dict' and payload[1] in (b'source', b'player_index')
+        assert 1 <= int(payload[2]) <= 7
+  assert 'player_cleaned' in names and 'zap' in names
+  assert len(seen) > 0 and all(isinstance(e, tuple) for e in seen)
