@@ -65,10 +65,11 @@ typedef struct mp_buffers {
   int32_t grid_layers, grid_cells, grid_cells_padded;
   double* timestep_packed;  /* f64 [B][P+2]: reward[0..P), discount, step type -- one buffer for the per-step all-gather */
   /* Events of the current step (the events:add calls of avatar_library.lua:661,1070,1088,
-   * component_library.lua:996, clean_up/components.lua:152,402, territory/components.lua:133,168). Row = (type, a, b)
+   * component_library.lua:996, clean_up/components.lua:152,402, territory/components.lua:133,168, coins/components.lua:133). Row = (type, a, b)
    * with 1-based player indices: 1 zap(source, target), 2 edible_consumed(player), 3 player_cleaned(player),
    * 4 claimed_resource(player), 5 destroyed_resource(player), 6 sanctioning(source, target),
-   * 7 removal_due_to_sanctioning(source, target). Rows of one step are in no particular order; event_count may
+   * 7 removal_due_to_sanctioning(source, target), 8 coin_consumed(player, 1 if the coin matched the player's type else 0;
+   * coins/components.lua:133-137). Rows of one step are in no particular order; event_count may
    * exceed max_events, in which case only the first max_events rows were kept. */
   int32_t* events;          /* i32 [B][max_events][3] */
   int32_t* event_count;     /* i32 [B] */

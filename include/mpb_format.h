@@ -72,13 +72,13 @@ enum MpbMeta {
   MPB_META_COUNT = 32
 };
 
-enum MpbFamily { MPB_FAMILY_CLEAN_UP = 1, MPB_FAMILY_COMMONS_HARVEST = 2, MPB_FAMILY_TERRITORY = 3 };
+enum MpbFamily { MPB_FAMILY_CLEAN_UP = 1, MPB_FAMILY_COMMONS_HARVEST = 2, MPB_FAMILY_TERRITORY = 3, MPB_FAMILY_COINS = 4 };
 
 /* Primitive action fields (columns of section "action_table"). */
 enum MpbActionField { MPB_ACT_MOVE = 0, MPB_ACT_TURN = 1, MPB_ACT_FIRE_ZAP = 2, MPB_ACT_FIRE_2 = 3 /* fireClean | fireClaim */ };
 
 /* Per-player scalar observation ids (section "scalar_obs", int32[N_SCALAR_OBS]). */
-enum MpbScalarObs { MPB_OBS_READY_TO_SHOOT = 0, MPB_OBS_NUM_OTHERS_WHO_CLEANED = 1 };
+enum MpbScalarObs { MPB_OBS_READY_TO_SHOOT = 0, MPB_OBS_NUM_OTHERS_WHO_CLEANED = 1, MPB_OBS_MISMATCHED_COIN_BY_PARTNER = 2 };
 
 /* Component type ids (section "comps", column 0). */
 enum MpbComp {
@@ -123,6 +123,13 @@ enum MpbComp {
   MPB_C_TERRITORY_TASTE = 31,  /* ip0 role (0 none, 1 rewarded_per_claim, 2 rewarded_per_claim_only); dp0 rewardAmount, dp1 firstClaimRewardMultiplier */
   MPB_C_ROLE = 32,             /* inert: the role string only matters to RoleBasedRewardTile */
   MPB_C_ROLE_BASED_REWARD_TILE = 33, /* inert: the compiler rejects configs in which an avatar's role is rewarded */
+  MPB_C_COIN = 34,             /* ip0 wait state, ip1 terminateEpisode, ip2 coinsToTerminateEpisode;
+                                  dp0 rewardSelfForMatch, dp1 rewardSelfForMismatch, dp2 rewardOtherForMatch, dp3 rewardOtherForMismatch */
+  MPB_C_CHOICE_COIN_REGROW = 35, /* ip0 liveStateA, ip1 liveStateB, ip2 wait state; dp0 regrowRate */
+  MPB_C_GLOBAL_COIN_COLLECTION_TRACKER = 36,
+  MPB_C_PLAYER_COIN_TYPE = 37, /* ip0 0 / 1: the player's coin type is the coin's liveStateA / liveStateB */
+  MPB_C_COINS_ROLE = 38,       /* dp0..3 multipliers of the four Coin rewards (self match, self mismatch, other match, other mismatch) */
+  MPB_C_PARTNER_TRACKER = 39,
   MPB_C_COUNT
 };
 

@@ -41,7 +41,7 @@ META = dict(FAMILY=0, W=1, H=2, L=3, P=4, SPRITE_SIZE=5, TOPOLOGY=6,
             VIEW_FORWARD=17, VIEW_BACKWARD=18, N_ACTIONS=19,
             N_ACTION_FIELDS=20, OOB_SPRITE=21, OOV_SPRITE=22, N_SCALAR_OBS=23)
 META_COUNT = 32
-FAMILY = {'clean_up': 1, 'commons_harvest': 2, 'territory': 3}
+FAMILY = {'clean_up': 1, 'commons_harvest': 2, 'territory': 3, 'coins': 4}
 COMP = dict(StateManager=1, Transform=2, Appearance=3, BeamBlocker=4, Edible=5,
             AppleGrow=6, DirtTracker=7, DirtCleaning=8, Avatar=9, Zapper=10,
             ReadyToShootObservation=11, Cleaner=12, Taste=13,
@@ -51,11 +51,14 @@ COMP = dict(StateManager=1, Transform=2, Appearance=3, BeamBlocker=4, Edible=5,
             DensityRegrow=23, LocationObserver=24, AllBeamBlocker=25,
             Resource=26, ResourceClaimer=27, RewardIndicator=28, Paintbrush=29,
             GraduatedSanctionsMarking=30, TerritoryTaste=31, Role=32,
-            RoleBasedRewardTile=33)
+            RoleBasedRewardTile=33, Coin=34, ChoiceCoinRegrow=35,
+            GlobalCoinCollectionTracker=36, PlayerCoinType=37, CoinsRole=38,
+            PartnerTracker=39)
 COMP_NI, COMP_ND = 16, 6
 ACTION_FIELDS = {'move': 0, 'turn': 1, 'fireZap': 2, 'fireClean': 3,
                  'fireClaim': 3}
-SCALAR_OBS = {'READY_TO_SHOOT': 0, 'NUM_OTHERS_WHO_CLEANED_THIS_STEP': 1}
+SCALAR_OBS = {'READY_TO_SHOOT': 0, 'NUM_OTHERS_WHO_CLEANED_THIS_STEP': 1,
+              'MISMATCHED_COIN_COLLECTED_BY_PARTNER': 2}
 COMPASS = {'N': 0, 'E': 1, 'S': 2, 'W': 3}
 BASE_LAYERS = ['logic', 'alternateLogic', 'background', 'lowerPhysical',
                'upperPhysical', 'overlay', 'superOverlay']
@@ -308,6 +311,7 @@ class WorldModel:
         if ch in cpm:
           _expand_prefab(cpm[ch], sim['prefabs'], objs, x, y, rng)
     self.objects_cfg = objs
+    self._prefabs = sim.get('prefabs', {})
     self.avatar_roles = set()
     self.rewarded_roles = set()
 
@@ -530,6 +534,28 @@ class WorldModel:
         ip[9] = int(kw['gameFramesPerAnimationFrame'])
         ip[10] = int(kw['loop'])
         ip[11] = int(kw.get('randomStartFrame', False))
+      elif name == 'Role' and self.family == 'coins':
+        # coins/components.lua Role: multipliers on the four Coin rewards.
+        name = 'CoinsRole'
+        dp[0] = float(kw.get('multiplyRewardSelfForMatch', 1.0))
+        dp[1] = float(kw.get('multiplyRewardSelfForMismatch', 1.0))
+        dp[2] = float(kw.get('multiplyRewardOtherForMatch', 1.0))
+        dp[3] = float(kw.get('multiplyRewardOtherForMismatch', 1.0))
+      elif name == 'Coin':  # coins/components.lua Coin
+        ip[0] = si(kw['waitState'])
+        ip[1] = int(bool(kw.get('terminateEpisode', False)))
+        ip[2] = int(kw.get('coinsToTerminateEpisode', -1))
+        dp[0] = float(kw['rewardSelfForMatch'])
+        dp[1] = float(kw['rewardSelfForMismatch'])
+        dp[2] = float(kw['rewardOtherForMatch'])
+        dp[3] = float(kw['rewardOtherForMismatch'])
+      elif name == 'ChoiceCoinRegrow':  # coins/components.lua ChoiceCoinRegrow
+        ip[0], ip[1], ip[2] = si(kw['liveStateA']), si(kw['liveStateB']), si(kw['waitState'])
+        dp[0] = float(kw['regrowRate'])
+      elif name == 'PlayerCoinType':
+        # 0 / 1 = the coin prefab's liveStateA / liveStateB (Coin:onEnter compares the type with the coin's state name)
+        regrow = _first(self._prefabs['coin']['components'], 'ChoiceCoinRegrow')['kwargs']
+        ip[0] = [regrow['liveStateA'], regrow['liveStateB']].index(kw['coinType'])
       elif name == 'Role':
         # component_library.lua Role: a string the avatar carries; only RoleBasedRewardTile reads it.
         self.avatar_roles.add(str(kw.get('role', 'none')))
@@ -865,6 +891,57 @@ def _commons_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
   sections['ch_nbr'] = nbr
 
 
+def _coins_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
+  """SoA tables for the coins step kernel (lua/levels/coins/components.lua)."""
+  W, P = model.W, model.num_players
+  if P != 2:
+    raise NotImplementedError('coins supports exactly two players (coins/components.lua:93-96)')
+  coins = []
+  for oid, ci in _objects_with(model, 'Coin'):
+    kid, x, y, orient, st = model.objects[oid]
+    coins.append((oid, y * W + x, kid, ci, st))
+  kid_c, ci_c = coins[0][2], coins[0][3]
+  if any(c[2] != kid_c for c in coins):
+    raise NotImplementedError('heterogeneous coin prefabs')
+  kc = model.kinds[kid_c]
+  coin_i, coin_d = model.comps_i[ci_c][1:], model.comps_d[ci_c]
+  regrow = [c for c in range(kc[2], kc[2] + kc[3]) if model.comps_i[c][0] == COMP['ChoiceCoinRegrow']][0]
+  ri, rd = model.comps_i[regrow][1:], model.comps_d[regrow]
+  if ri[2] != coin_i[0]:
+    raise NotImplementedError('Coin and ChoiceCoinRegrow wait states differ')
+  if any(c[4] != coin_i[0] for c in coins):
+    raise NotImplementedError('coins that do not start in the wait state')
+  live_a, live_b = model.states[kc[0] + ri[0]], model.states[kc[0] + ri[1]]
+  if live_a[0] != live_b[0]:
+    raise NotImplementedError('coin types on different layers')
+  def avatar_row(comp):
+    rows = []
+    for oid in model.avatar_objs:
+      k = model.kinds[model.objects[oid][0]]
+      ci = [c for c in range(k[2], k[2] + k[3]) if model.comps_i[c][0] == COMP[comp]][0]
+      rows.append((model.comps_i[ci][1:], model.comps_d[ci]))
+    return rows
+  types = [r[0][0] for r in avatar_row('PlayerCoinType')]
+  roles = [r[1] for r in avatar_row('CoinsRole')]
+  scene_k = model.kinds[model.objects[0][0]]
+  end = [c for c in range(scene_k[2], scene_k[2] + scene_k[3])
+         if model.comps_i[c][0] == COMP['StochasticIntervalEpisodeEnding']][0]
+  ei, ed = model.comps_i[end][1:], model.comps_d[end]
+  ip = np.zeros(48, np.int32)
+  dp = np.zeros(16, np.float64)
+  ip[0:8] = [len(coins), live_a[0], live_a[1], live_b[1], coin_i[1], coin_i[2], ei[0], ei[1]]
+  ip[8:10] = types
+  dp[0] = rd[0]
+  dp[1] = ed[0]
+  # the four rewards as each collecting player pays them: base reward x that player's Role multiplier
+  for p in range(2):
+    for k in range(4):
+      dp[4 + p * 4 + k] = coin_d[k] * roles[p][k]
+  sections['co_ip'] = ip
+  sections['co_dp'] = dp
+  sections['co_coin'] = np.array([[c[0], c[1]] for c in coins], np.int32)
+
+
 def _territory_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
   """SoA tables for the territory step kernel."""
   W, P = model.W, model.num_players
@@ -1036,6 +1113,8 @@ def compile_settings(settings: Mapping[str, Any],
     _commons_tables(model, sections)
   elif model.family == 'territory':
     _territory_tables(model, sections)
+  elif model.family == 'coins':
+    _coins_tables(model, sections)
   info = dict(
       level=model.level, family=model.family, layers=model.layers,
       sprites=model.sprites.names, groups=model.groups,
@@ -1059,5 +1138,13 @@ def compile_substrate(name: str, roles: Optional[Sequence[str]] = None,
   """Compiles a named reference substrate (needs a reference checkout)."""
   config = load_reference_config(name, root)
   roles = tuple(roles) if roles is not None else tuple(config.default_player_roles)
-  settings = config.lab2d_settings_builder(roles=roles, config=config)
+  # Some builders draw from Python's global `random` (coins.py:45-84,488: map size and the two coin types):
+  # with a build seed the draw is reproducible (policy A.20), without one it is the reference's behaviour.
+  state = random.getstate()
+  try:
+    if build_seed is not None:
+      random.seed(build_seed)
+    settings = config.lab2d_settings_builder(roles=roles, config=config)
+  finally:
+    random.setstate(state)
   return compile_settings(settings, config, build_seed)

@@ -92,6 +92,12 @@ struct Tables {
   const int16_t* sprite_map;   // [P+1][n_total]
   const uint8_t* sprite_opaque;  // [n_total] bit 0: every pixel alpha 255 and never remapped; bit 1: remapped for some viewer
   const uint8_t* sprite_pair;    // [n_total][n_total] pre-merged sprite for (opaque base, sprite on top) or 0
+  // coins family (step_coins.cuh); the coins reuse ch_apple / apple_of_cell / apple_layer
+  int coin_sprite[2];          // sprite of coin type 0 / 1 (liveStateA / liveStateB)
+  int coin_type[2];            // PlayerCoinType of each player
+  double coin_reward[2][4];    // per collecting player: self match, self mismatch, other match, other mismatch
+  double coin_rate;            // ChoiceCoinRegrow regrowRate
+  int coin_terminate, coin_terminate_n;
 };
 
 struct State {
@@ -125,7 +131,7 @@ struct State {
 // the order of oracle/mp_oracle.c; player indices are 1-based as in Lua.
 #define MP_MAX_EVENTS 64
 enum { EV_ZAP = 1, EV_EDIBLE_CONSUMED = 2, EV_PLAYER_CLEANED = 3, EV_CLAIMED_RESOURCE = 4, EV_DESTROYED_RESOURCE = 5,
-       EV_SANCTIONING = 6, EV_REMOVAL = 7 };
+       EV_SANCTIONING = 6, EV_REMOVAL = 7, EV_COIN_CONSUMED = 8 /* a = player, b = 1 match / 0 mismatch */ };
 
 // Called by the one lane that owns the event. Lanes append concurrently, so the order within a
 // step is unspecified (hosts sort); the per-env counter is zeroed at kernel entry.

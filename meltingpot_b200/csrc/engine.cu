@@ -17,6 +17,7 @@
 #include "step_clean_up.cuh"
 #include "step_commons.cuh"
 #include "step_territory.cuh"
+#include "step_coins.cuh"
 
 namespace {
 
@@ -159,7 +160,7 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   if (T.topology == 1 && (T.view_l + T.view_r + 1 > T.W || T.view_f + T.view_b + 1 > T.H || T.view_l + T.view_r + 1 > T.H || T.view_f + T.view_b + 1 > T.W))
     return fail(MP_E_UNSUPPORTED, "TORUS map smaller than the view window");
   for (int k = 0; k < T.n_scalar; ++k) T.scalar_obs[k] = scalar_obs.data[k];
-  if (E->family != MPB_FAMILY_CLEAN_UP && E->family != MPB_FAMILY_COMMONS_HARVEST && E->family != MPB_FAMILY_TERRITORY) return fail(MP_E_UNSUPPORTED, "substrate family %d has no CUDA state-transition kernel yet", E->family);
+  if (E->family != MPB_FAMILY_CLEAN_UP && E->family != MPB_FAMILY_COMMONS_HARVEST && E->family != MPB_FAMILY_TERRITORY && E->family != MPB_FAMILY_COINS) return fail(MP_E_UNSUPPORTED, "substrate family %d has no CUDA state-transition kernel yet", E->family);
 
   // ---- avatars ---------------------------------------------------------------------------------
   T.avatar_layer = av_table.data[2];
@@ -257,6 +258,24 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
     v_apple.assign(ch_apple.data, ch_apple.data + ch_apple.count);
     std::vector<int32_t> v_nbr(ch_nbr.data, ch_nbr.data + ch_nbr.count);
     if ((rc = E->upload(v_apple, &T.ch_apple)) || (rc = E->upload(v_nbr, &T.ch_nbr))) return rc;
+  }
+  else if (E->family == MPB_FAMILY_COINS) {
+    Section<int32_t> co_ip, co_coin;
+    Section<double> co_dp;
+    NEED(co_ip, MPB_I32) NEED(co_dp, MPB_F64) NEED(co_coin, MPB_I32)
+    const int32_t* ip = co_ip.data; const double* dp = co_dp.data;
+    if (T.P != 2) return fail(MP_E_UNSUPPORTED, "coins needs exactly two players (got %d)", T.P);
+    T.nA = ip[0]; T.apple_layer = ip[1]; T.coin_sprite[0] = ip[2]; T.coin_sprite[1] = ip[3];
+    T.coin_terminate = ip[4]; T.coin_terminate_n = ip[5]; T.end_min_frames = ip[6]; T.end_interval = ip[7];
+    T.coin_type[0] = ip[8]; T.coin_type[1] = ip[9];
+    if (T.nA > 2048) return fail(MP_E_UNSUPPORTED, "%d coins (max 2048)", T.nA);
+    if (T.end_interval < 1) return fail(MP_E_INVALID, "episode interval < 1");
+    T.coin_rate = dp[0]; T.end_prob = dp[1];
+    for (int p = 0; p < 2; ++p) for (int k = 0; k < 4; ++k) T.coin_reward[p][k] = dp[4 + p * 4 + k];
+    T.zap_layer = 0; T.zap_cooldown = 1;
+    v_apple.resize((size_t)T.nA * 4);
+    for (int k = 0; k < T.nA; ++k) { v_apple[k * 4] = co_coin.data[k * 2]; v_apple[k * 4 + 1] = co_coin.data[k * 2 + 1]; v_apple[k * 4 + 2] = 0; v_apple[k * 4 + 3] = -1; }
+    if ((rc = E->upload(v_apple, &T.ch_apple))) return rc;
   }
   else {  // MPB_FAMILY_TERRITORY
     Section<int32_t> tr_ip, tr_res, tr_player_sprites;
@@ -513,6 +532,7 @@ int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int 
   const int blocks = (E->B + 3) / 4;
   if (E->family == MPB_FAMILY_CLEAN_UP) k_step_clean_up<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
   else if (E->family == MPB_FAMILY_COMMONS_HARVEST) k_step_commons<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
+  else if (E->family == MPB_FAMILY_COINS) k_step_coins<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
   else k_step_territory<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
@@ -624,6 +644,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_clean_up, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_commons, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_territory, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_coins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
   if (ce != cudaSuccess) { mp_destroy(E); return fail(MP_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)); }
   mp_buffers& bf = E->buffers;
   bf.num_envs = num_envs; bf.num_players = T.P; bf.rgb_h = E->R.view_h * 8; bf.rgb_w = E->R.view_w * 8;

@@ -93,10 +93,10 @@ def load_library() -> ctypes.CDLL:
 
 
 EVENT_NAMES = {1: 'zap', 2: 'edible_consumed', 3: 'player_cleaned', 4: 'claimed_resource',
-               5: 'destroyed_resource', 6: 'sanctioning', 7: 'removal_due_to_sanctioning'}
+               5: 'destroyed_resource', 6: 'sanctioning', 7: 'removal_due_to_sanctioning', 8: 'coin_consumed'}
 # argument names of each event's dict payload (second one unused for single-argument events)
 EVENT_FIELDS = {1: ('source', 'target'), 2: ('player_index',), 3: ('player_index',), 4: ('player_index',),
-                5: ('player_index',), 6: ('source', 'target'), 7: ('source', 'target')}
+                5: ('player_index',), 6: ('source', 'target'), 7: ('source', 'target'), 8: ('player_index', 'matched')}
 
 
 class EngineError(RuntimeError):

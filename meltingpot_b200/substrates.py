@@ -16,11 +16,13 @@ PRECOMPILED = {
     'territory__inside_out': (5,),
     'commons_harvest__closed': (7,),
     'commons_harvest__partnership': (7,),
+    'coins': (2,),
 }
 
-# Substrates whose maps hold 'choice' prefabs (prefab_utils.lua:63-65): the reference draws them per env
-# instance at build time; a compiled blob fixes one draw (policy A.20), made with this seed.
-BUILD_SEEDS = {'territory__inside_out': 0}
+# Substrates with build-time randomness: 'choice' prefabs drawn per env instance (prefab_utils.lua:63-65), or
+# a builder that draws from Python's `random` (coins.py:45-84,488: map size, coin colours). A compiled blob
+# fixes one draw (policy A.20), made with this seed.
+BUILD_SEEDS = {'territory__inside_out': 0, 'coins': 0}
 
 
 def blob_path(name: str, num_players: int) -> str:

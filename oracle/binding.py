@@ -84,7 +84,7 @@ def _ptr(arr, ctype):
 
 
 EVENT_NAMES = {1: 'zap', 2: 'edible_consumed', 3: 'player_cleaned', 4: 'claimed_resource',
-               5: 'destroyed_resource', 6: 'sanctioning', 7: 'removal_due_to_sanctioning'}
+               5: 'destroyed_resource', 6: 'sanctioning', 7: 'removal_due_to_sanctioning', 8: 'coin_consumed'}
 
 
 class OracleEnv:

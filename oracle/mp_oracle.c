@@ -84,18 +84,21 @@ typedef struct {
   int paired_resource;                               /* RewardIndicator */
   int claim_cool;                                    /* ResourceClaimer */
   int level, time_not_initial, marking_avatar;       /* GraduatedSanctionsMarking */
+  int partner_match, partner_mismatch;               /* PartnerTracker (coins) */
+  int coins_cumulative;                              /* GlobalCoinCollectionTracker.cumulativeCoinsCollected(player) */
 } Obj;
 
 enum { ACT_SET_STATE, ACT_TURN, ACT_MOVE_REL, ACT_TELEPORT_GROUP, ACT_BEAM, ACT_TELEPORT, ACT_SET_ORIENT };
 typedef struct { int type, obj, a, b, c; } Action;
 
-enum { EV_ZAP = 1, EV_EDIBLE_CONSUMED = 2, EV_PLAYER_CLEANED = 3, EV_CLAIMED_RESOURCE = 4, EV_DESTROYED_RESOURCE = 5, EV_SANCTIONING = 6, EV_REMOVAL = 7 };
+enum { EV_ZAP = 1, EV_EDIBLE_CONSUMED = 2, EV_PLAYER_CLEANED = 3, EV_CLAIMED_RESOURCE = 4, EV_DESTROYED_RESOURCE = 5, EV_SANCTIONING = 6, EV_REMOVAL = 7,
+       EV_COIN_CONSUMED = 8 /* a = player, b = 1 match / 0 mismatch */ };
 typedef struct { int type, a, b; } Event;
 
 enum { /* updater function ids */
   UF_AVATAR_MOVE, UF_ZAP, UF_RESPAWN, UF_CLEAN, UF_CLEANER_RESET, UF_TASTE_RESET, UF_NONSELF_GET,
   UF_NONSELF_RESET, UF_GLOBAL_RESET, UF_EPISODE_END, UF_ANIMATION, UF_SPROUT,
-  UF_PAINTBRUSH, UF_CLAIM, UF_PROVIDE_REWARDS, UF_RELEASE_CLAIM, UF_MARKING_RECOVERY
+  UF_PAINTBRUSH, UF_CLAIM, UF_PROVIDE_REWARDS, UF_RELEASE_CLAIM, UF_MARKING_RECOVERY, UF_COIN_REGROW
 };
 typedef struct { int priority, comp_type, fn, seq; } Updater;
 
@@ -183,6 +186,29 @@ static void on_enter(OrEnv* e, int target, int initiator) {
       add_event(e, EV_EDIBLE_CONSUMED, avc->ip[0] + 1, 0);
       enqueue(e, ACT_SET_STATE, target, ed->ip[1], 0, 0);
     }
+  }
+  const CompDef* coin = find_comp(e, t, MPB_C_COIN);
+  if (coin && t->state != coin->ip[0]) { /* Coin:onEnter -- coins/components.lua:87-160 */
+    const CompDef* avc = find_comp(e, ini, MPB_C_AVATAR);
+    const CompDef* role = find_comp(e, ini, MPB_C_COINS_ROLE);
+    const CompDef* regrow = find_comp(e, t, MPB_C_CHOICE_COIN_REGROW);
+    const int me = avc->ip[0], partner = 1 - me;
+    const int my_type_state = find_comp(e, ini, MPB_C_PLAYER_COIN_TYPE)->ip[0] == 0 ? regrow->ip[0] : regrow->ip[1];
+    const int match = t->state == my_type_state;
+    Obj* other = &e->obj[e->avatar_obj[partner]];
+    if (match) {
+      avatar_add_reward(e, ini, coin->dp[0] * role->dp[0]);  /* Role:getRewardSelfForMatch :231-235 */
+      avatar_add_reward(e, other, coin->dp[2] * role->dp[2]); /* Coin:rewardOthers :74-85 (two players) */
+      other->partner_match = 1;                               /* PartnerTracker:reportMatch :324-326 */
+    } else {
+      avatar_add_reward(e, ini, coin->dp[1] * role->dp[1]);
+      avatar_add_reward(e, other, coin->dp[3] * role->dp[3]);
+      other->partner_mismatch = 1;                            /* PartnerTracker:reportMismatch :328-330 */
+    }
+    add_event(e, EV_COIN_CONSUMED, me + 1, match);
+    enqueue(e, ACT_SET_STATE, target, coin->ip[0], 0, 0);
+    ini->coins_cumulative += 1;
+    if (coin->ip[1] && ini->coins_cumulative >= coin->ip[2]) e->cont = 0; /* simulation:endEpisode() */
   }
 }
 
@@ -640,6 +666,11 @@ static void run_updater(OrEnv* e, const Updater* u, int oi) {
       uint32_t w[4]; rng(e, RS_OBJECT, oi, w);
       if (u01(w[0], w[1]) < c->dp[1 + idx]) enqueue(e, ACT_SET_STATE, oi, c->ip[0], 0, 0); /* canRegrowIfOccupied */
     } break;
+    case UF_COIN_REGROW: { /* ChoiceCoinRegrow (coins/components.lua:183-194): state = waitState, probability = regrowRate */
+      if (o->state != c->ip[2]) break;
+      uint32_t w[4]; rng(e, RS_OBJECT, oi, w);
+      if (u01(w[0], w[1]) < c->dp[0]) enqueue(e, ACT_SET_STATE, oi, c->ip[pick(w[2], 2u)], 0, 0); /* random:choice(liveStates) */
+    } break;
     case UF_ANIMATION: { /* component_library.lua:1070-1094: one updater per state, startFrame */
       if (age < c->ip[9]) break;
       int n = c->ip[0];
@@ -677,6 +708,7 @@ static void build_updaters(OrEnv* e) {
         case MPB_C_STOCHASTIC_INTERVAL_EPISODE_ENDING: add_updater(e, 100, MPB_C_STOCHASTIC_INTERVAL_EPISODE_ENDING, UF_EPISODE_END); break;
         case MPB_C_ANIMATION: add_updater(e, 100, MPB_C_ANIMATION, UF_ANIMATION); break;
         case MPB_C_DENSITY_REGROW: add_updater(e, 10, MPB_C_DENSITY_REGROW, UF_SPROUT); break;
+        case MPB_C_CHOICE_COIN_REGROW: add_updater(e, 100, MPB_C_CHOICE_COIN_REGROW, UF_COIN_REGROW); break; /* default priority (updater_registry.lua:47) */
         case MPB_C_PAINTBRUSH: add_updater(e, 130, MPB_C_PAINTBRUSH, UF_PAINTBRUSH); break;
         case MPB_C_RESOURCE_CLAIMER: add_updater(e, 100, MPB_C_RESOURCE_CLAIMER, UF_CLAIM); break;
         case MPB_C_RESOURCE: add_updater(e, 100, MPB_C_RESOURCE, UF_PROVIDE_REWARDS); add_updater(e, 2, MPB_C_RESOURCE, UF_RELEASE_CLAIM); break;
@@ -721,6 +753,7 @@ static void grid_update(OrEnv* e) {
 /* BaseSimulation:update -- base_simulation.lua:476-486 (preUpdate all, then update all). */
 static void simulation_update(OrEnv* e) {
   for (int p = 0; p < e->P; ++p) e->obj[e->avatar_obj[p]].reward = 0.0; /* Avatar:preUpdate :330-332 */
+  for (int p = 0; p < e->P; ++p) { Obj* a = &e->obj[e->avatar_obj[p]]; a->partner_match = 0; a->partner_mismatch = 0; } /* PartnerTracker:preUpdate (coins/components.lua:303-306) */
   for (int oi = 0; oi < e->n_obj; ++oi) {
     Obj* o = &e->obj[oi];
     const KindDef* k = kind_of(e, o);
@@ -1013,6 +1046,7 @@ void oracle_get_scalar_obs(const OrEnv* e, double* out) {
         const CompDef* z = find_comp(e, o, MPB_C_ZAPPER);
         if (avatar_is_alive(e, o)) v = fmax(1.0 - (double)o->zap_cool / (double)z->ip[0], 0.0);
       } else if (e->scalar_obs[k] == MPB_OBS_NUM_OTHERS_WHO_CLEANED) v = (double)o->num_others_cleaned;
+      else if (e->scalar_obs[k] == MPB_OBS_MISMATCHED_COIN_BY_PARTNER) v = (double)o->partner_mismatch;
       out[p * e->n_scalar + k] = v;
     }
   }

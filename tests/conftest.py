@@ -71,3 +71,9 @@ def territory_inside_out_blob():
 def commons_partnership_blob():
   from meltingpot_b200 import substrates
   return substrates.load_blob('commons_harvest__partnership', ('default',) * 7)
+
+
+@pytest.fixture(scope='session')
+def coins_blob():
+  from meltingpot_b200 import substrates
+  return substrates.load_blob('coins', ('default',) * 2)

@@ -183,3 +183,9 @@ def test_events_reach_the_dm_env_api(clean_up_blob):
         assert 1 <= int(payload[2]) <= 7
   assert 'player_cleaned' in names and 'zap' in names
   assert len(seen) > 0 and all(isinstance(e, tuple) for e in seen)
+
+
+def test_coins_random_rollout(coins_blob, oracle):
+  # the eighth substrate of the sweep; two players, no beams, coin_consumed events.
+  stats = parity.compare_rollout(coins_blob, oracle, num_envs=24, steps=900, seed=31, pixels_every=4)
+  assert stats['events'] > 30

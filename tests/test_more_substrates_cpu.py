@@ -16,7 +16,7 @@ from meltingpot_b200 import substrate
 from meltingpot_b200 import substrates
 
 
-CASES = [('territory__open', 9), ('territory__inside_out', 5), ('commons_harvest__closed', 7), ('commons_harvest__partnership', 7)]
+CASES = [('territory__open', 9), ('territory__inside_out', 5), ('commons_harvest__closed', 7), ('commons_harvest__partnership', 7), ('coins', 2)]
 
 
 def _tables(blob):

@@ -18,6 +18,7 @@ CONFIGS = [
     ('territory__inside_out', 5, 4096),
     ('commons_harvest__closed', 7, 4096),
     ('commons_harvest__partnership', 7, 4096),
+    ('coins', 2, 8192),
 ]
 PEAK = 6561.6
 if os.path.exists('MEASURED_PEAKS.json'):
