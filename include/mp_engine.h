@@ -136,6 +136,10 @@ int mp_state_size(mp_handle h, uint64_t* bytes);
 int mp_state_save(mp_handle h, void* host_dst, void* stream);
 int mp_state_load(mp_handle h, const void* host_src, void* stream);
 
+/* Diagnostic: how the renderer was laid out for this substrate: teams per CTA, threads per team, log2 of the pixel
+ * rows per WORLD.RGB strip, shared memory bytes, atlas sprites, record stride (u16), staging bytes per warp, grid bytes. */
+int mp_debug_render_plan(mp_handle h, int32_t out[8]);
+
 /* Diagnostic: the renderer's sprite tables. *n_total = atlas sprites including the pre-merged ones;
  * pair[n_total * n_total] = pre-merged sprite for (bottom, top) or 0; flags[n_total] bit 0 opaque,
  * bit 1 remapped per viewer. Either array may be NULL (call once for n_total, then again). */

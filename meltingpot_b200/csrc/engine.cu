@@ -58,6 +58,7 @@ bool get_section(const void* blob, size_t n, const char* name, int dtype, Sectio
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+constexpr int kRenderSmemLimit = 227 * 1024 - 2560;  // dynamic shared memory: the 227 KB opt-in maximum less k_render's static arrays
 constexpr int kMaxAtlasSprites = 96;  // sprites incl. pre-merged ones kept in shared memory by k_render
 
 // Beam footprint in visiting order (policy A.8): centre ray, then for each side the lateral cells
@@ -509,22 +510,33 @@ int build_plan(mp_engine* E) {
   R.off_pair = off; off += round_up(R.n_total * R.n_total, 128);
   R.off_map = off; off += round_up((T.P + 1) * R.n_total * 2, 128);
   R.off_team0 = off;
-  // the largest team (most warps in flight) whose staging buffers still fit, with WORLD.RGB strips of 4 pixel
-  // rows if possible and of 2 otherwise
+  // Teams per CTA x warps per team x WORLD.RGB strip height: among the layouts that fit in shared memory, the one
+  // with the most useful warps in flight. A team draws one env at a time, so its warps share that env's strips; with
+  // few strips per warp the end-of-env barrier and the last straggling strip weigh more (score below).
   R.smem_bytes = 1 << 30;
-  for (int tt = TEAM_THREADS; tt >= 128 && R.smem_bytes > 227 * 1024; tt -= 128)
-    for (int wlog = 2; wlog >= 1 && R.smem_bytes > 227 * 1024; --wlog) {
-      R.wstrip_log2 = wlog;
-      R.team_threads = tt;
-      R.stage_bytes = RENDER_SLOTS * round_up(std::max(R.view_w * 192, T.W * 24 * (1 << wlog)), 128);
-      int toff = 0;
-      R.toff_grid = toff; toff += round_up(R.grid_bytes, 128);
-      R.toff_rec = toff; toff += round_up(T.cells * R.rec_stride * 2, 128);
-      R.toff_stage = toff; toff += (tt / 32) * R.stage_bytes;
-      R.team_stride = toff;
-      R.smem_bytes = R.off_team0 + RENDER_TEAMS * R.team_stride;
+  double best = -1.0;
+  for (int teams = 2; teams <= RENDER_MAX_TEAMS; ++teams)
+    for (int warps = TEAM_THREADS / 32; warps >= 4; --warps) {
+      if (teams * warps > RENDER_MAX_THREADS / 32) continue;
+      for (int wlog = 2; wlog >= 1; --wlog) {
+        const int stage = RENDER_SLOTS * round_up(std::max(R.view_w * 192, T.W * 24 * (1 << wlog)), 128);
+        const int team_bytes = round_up(R.grid_bytes, 128) + round_up(T.cells * R.rec_stride * 2, 128) + warps * stage;
+        const int total = R.off_team0 + teams * team_bytes;
+        if (total > kRenderSmemLimit) continue;
+        const double items = T.P * R.view_h + (8 >> wlog) * T.H, per_warp = items / warps;
+        // (constants fitted to measurements on the eight substrates: about three strips' worth of idle time per env and
+        //  warp, 2-row WORLD.RGB strips ~15 % slower than 4-row ones, a small cost per extra team)
+        const double score = teams * warps * per_warp / (per_warp + 3.0) * (wlog == 2 ? 1.0 : 0.85) * (1.0 - 0.01 * teams);
+        if (score > best + 1e-9) {
+          best = score;
+          R.n_teams = teams; R.team_threads = warps * 32; R.wstrip_log2 = wlog; R.stage_bytes = stage;
+          R.toff_grid = 0; R.toff_rec = round_up(R.grid_bytes, 128);
+          R.toff_stage = R.toff_rec + round_up(T.cells * R.rec_stride * 2, 128);
+          R.team_stride = team_bytes; R.smem_bytes = total;
+        }
+      }
     }
-  if (R.smem_bytes > 227 * 1024) return fail(MP_E_UNSUPPORTED, "render kernel needs %d B of shared memory (> 227 KB)", R.smem_bytes);
+  if (R.smem_bytes > kRenderSmemLimit) return fail(MP_E_UNSUPPORTED, "render kernel needs %d B of shared memory (> 227 KB)", R.smem_bytes);
   return MP_OK;
 }
 
@@ -541,7 +553,7 @@ int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int 
 
 int launch_render(mp_engine* E, cudaStream_t st) {
   if (!(E->flags & (MP_FLAG_RENDER_WORLD | MP_FLAG_RENDER_PLAYERS))) return MP_OK;
-  const int blocks = std::min((E->B + RENDER_TEAMS - 1) / RENDER_TEAMS, E->sm_count);
+  const int blocks = std::min((E->B + E->R.n_teams - 1) / E->R.n_teams, E->sm_count);
   RenderPlan R = E->R;
   const Tables& T = E->T;
   R.n_player_items = (E->flags & MP_FLAG_RENDER_PLAYERS) ? T.P * R.view_h : 0;
@@ -549,7 +561,7 @@ int launch_render(mp_engine* E, cudaStream_t st) {
   R.prow_bytes = R.view_w * 24; R.wrow_bytes = T.W * 24;
   R.pitem_bytes = R.prow_bytes * 8; R.witem_bytes = R.wrow_bytes << R.wstrip_log2;
   R.h_oob = 0x8000 | (T.oob_sprite * 4); R.h_oov = 0x8000 | (T.oov_sprite * 4);
-  E->render_fn<<<blocks, RENDER_TEAMS * R.team_threads, R.smem_bytes, st>>>(E->T, E->S, R, E->flags);
+  E->render_fn<<<blocks, R.n_teams * R.team_threads, R.smem_bytes, st>>>(E->T, E->S, R, E->flags);
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;
@@ -781,6 +793,14 @@ int mp_state_load(mp_handle h, const void* host_src, void* stream) {
 int mp_launch_count(mp_handle h, uint64_t* out) {
   if (!h || !out) return fail(MP_E_INVALID, "null argument");
   *out = h->launches;
+  return MP_OK;
+}
+
+int mp_debug_render_plan(mp_handle h, int32_t out[8]) {
+  if (!h || !out) return fail(MP_E_INVALID, "mp_debug_render_plan: null argument");
+  const RenderPlan& R = h->R;
+  const int32_t v[8] = {R.n_teams, R.team_threads, R.wstrip_log2, R.smem_bytes, R.n_total, R.rec_stride, R.stage_bytes, R.grid_bytes};
+  memcpy(out, v, sizeof v);
   return MP_OK;
 }
 

@@ -7,7 +7,7 @@
 // sprites, bottom-to-top alpha compositing in render order).
 //
 // HBM-bound by design: per env-step it reads the ~11 KB sprite grid and writes
-// P*88*88*3 + H*W*192 bytes of observations. One persistent CTA per SM hosts RENDER_TEAMS
+// P*88*88*3 + H*W*192 bytes of observations. One persistent CTA per SM hosts 2-4
 // independent teams of up to TEAM_THREADS threads (RenderPlan::team_threads, the most that fit in
 // shared memory next to the atlas) that share one shared-memory copy of the sprite atlas
 // (TMA-bulk-loaded once). Each team renders whole envs:
@@ -30,16 +30,14 @@
 
 #include "common.cuh"
 
-#ifndef RENDER_TEAMS
-#define RENDER_TEAMS 2
-#endif
+#define RENDER_MAX_TEAMS 4   // teams per CTA (RenderPlan::n_teams, 2..4)
+#define RENDER_MAX_THREADS 1024
 #ifndef TEAM_THREADS
 #define TEAM_THREADS 512
 #endif
 #ifndef RENDER_SLOTS
 #define RENDER_SLOTS 1  // staging slots per warp (32 warps per SM hide the TMA read of a single slot)
 #endif
-#define RENDER_THREADS (RENDER_TEAMS * TEAM_THREADS)
 
 struct RenderPlan {  // host-computed constants of the tiling
   int view_w, view_h;        // cells
@@ -56,7 +54,8 @@ struct RenderPlan {  // host-computed constants of the tiling
   int wstrip_log2;                      // log2 of the pixel rows per WORLD.RGB strip (1 or 2)
   int stage_bytes;                      // warp-private staging buffer: two slots, each one player cell-row or half a world cell-row
   int smem_bytes;
-  int team_threads;                     // threads per team (multiple of 32, <= TEAM_THREADS): what fits in shared memory
+  int team_threads;                     // threads per team (multiple of 32, <= TEAM_THREADS)
+  int n_teams;                          // teams per CTA (2..RENDER_MAX_TEAMS); n_teams * team_threads <= 1024
   // per-launch constants (depend on the render flags); kept here so that they are constant-bank operands, not registers
   int n_player_items, n_items;           // strips per env: player cell-rows, then WORLD.RGB strips
   int prow_bytes, wrow_bytes;            // one pixel row of a player image / of WORLD.RGB
@@ -233,20 +232,20 @@ struct ViewerInfo {  // per player, refreshed once per env
 // hand the slot to the TMA store engine. Three team barriers per env; everything else is warp-local.
 // Each lane handles NC cells per strip with the loads of all NC cells issued before any is packed.
 template <int NCP, int NCW>
-__global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S, RenderPlan R, uint32_t flags) {
+__global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, State S, RenderPlan R, uint32_t flags) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // [0] atlas, [1 + team] grid
   uint8_t* s_atlas = smem + R.off_atlas;
   const uint8_t* s_pair = smem + R.off_pair;                          // [n_total][n_total] merged sprite or 0
   int16_t* s_map = reinterpret_cast<int16_t*>(smem + R.off_map);      // [P+1][n_total]
   __shared__ uint8_t s_opaque[256];
-  __shared__ ViewerInfo s_view_all[RENDER_TEAMS][MP_MAX_PLAYERS];
-  __shared__ int s_next_item[RENDER_TEAMS];
+  __shared__ ViewerInfo s_view_all[RENDER_MAX_TEAMS][MP_MAX_PLAYERS];
+  __shared__ int s_next_item[RENDER_MAX_TEAMS];
 
   const int tid = threadIdx.x;
   int team = 0;
 #pragma unroll
-  for (int k = 1; k < RENDER_TEAMS; ++k) team += tid >= k * R.team_threads;
+  for (int k = 1; k < RENDER_MAX_TEAMS; ++k) team += tid >= k * R.team_threads;
   const int ttid = tid - team * R.team_threads;
   const int lane = tid & 31, twarp = ttid >> 5;
   uint8_t* s_team = smem + R.off_team0 + team * R.team_stride;
@@ -256,10 +255,10 @@ __global__ void __launch_bounds__(RENDER_THREADS, 1) k_render(Tables T, State S,
   ViewerInfo* s_view = s_view_all[team];
   uint64_t* gbar = &bar[1 + team];
 
-  const int n_streams = gridDim.x * RENDER_TEAMS;
-  const int first = blockIdx.x * RENDER_TEAMS + team;
+  const int n_streams = gridDim.x * R.n_teams;
+  const int first = blockIdx.x * R.n_teams + team;
   if (tid == 0) {
-    for (int i = 0; i < 1 + RENDER_TEAMS; ++i) mbar_init(&bar[i], 1);
+    for (int i = 0; i < 1 + R.n_teams; ++i) mbar_init(&bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (ttid == 0) s_next_item[team] = 0;

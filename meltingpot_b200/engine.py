@@ -23,7 +23,7 @@ MP_FLAG_DEFAULT = 3
 EXPORTED_SYMBOLS = (
     'mp_create', 'mp_destroy', 'mp_set_flags', 'mp_reset', 'mp_step',
     'mp_step_state', 'mp_render', 'mp_get_buffers', 'mp_step_host',
-    'mp_reset_host', 'mp_launch_count', 'mp_algorithmic_bytes', 'mp_debug_render_tables', 'mp_state_size', 'mp_state_save', 'mp_state_load',
+    'mp_reset_host', 'mp_launch_count', 'mp_algorithmic_bytes', 'mp_debug_render_tables', 'mp_debug_render_plan', 'mp_state_size', 'mp_state_save', 'mp_state_load',
     'mp_last_error', 'mp_version',
 )
 
@@ -85,6 +85,7 @@ def load_library() -> ctypes.CDLL:
   lib.mp_state_size.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
   lib.mp_state_save.argtypes = [vp, vp, vp]
   lib.mp_state_load.argtypes = [vp, vp, vp]
+  lib.mp_debug_render_plan.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
   lib.mp_debug_render_tables.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), vp, vp]
   lib.mp_last_error.restype = ctypes.c_char_p
   lib.mp_version.restype = ctypes.c_char_p
@@ -270,6 +271,13 @@ class Engine:
   def load_state(self, snapshot: bytes, stream=None) -> None:
     buf = ctypes.create_string_buffer(snapshot, len(snapshot))
     _check(self._lib.mp_state_load(self._h, buf, self._stream(stream)))
+
+  def render_plan(self):
+    """Layout the renderer chose for this substrate (diagnostic)."""
+    out = (ctypes.c_int32 * 8)()
+    _check(self._lib.mp_debug_render_plan(self._h, out))
+    keys = ('teams', 'team_threads', 'wstrip_log2', 'smem_bytes', 'atlas_sprites', 'rec_stride', 'stage_bytes', 'grid_bytes')
+    return dict(zip(keys, (int(v) for v in out)))
 
   def render_tables(self):
     """(pair[n, n], flags[n]) uint8 numpy arrays of the renderer's sprite tables (diagnostic)."""

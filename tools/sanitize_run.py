@@ -8,13 +8,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from meltingpot_b200 import engine, substrates
 
-for name, roles, n_act in (('clean_up', ('default',) * 7, 9), ('commons_harvest__open', ('default',) * 16, 8)):
+CASES = (('clean_up', 7, 9, 700), ('commons_harvest__open', 16, 8, 700), ('territory__rooms', 9, 9, 400),
+         ('territory__open', 9, 9, 400), ('coins', 2, 7, 700))
+for name, players, n_act, B in CASES:
+  roles = ('default',) * players
   blob = substrates.load_blob(name, roles)
-  eng = engine.Engine(blob, 300, seed=3)   # > 2 * 148 so that render teams process two envs each
+  eng = engine.Engine(blob, B, seed=3)   # more envs than render teams, so that teams process several envs each
   eng.reset()
   gen = torch.Generator(device='cuda').manual_seed(0)
-  for _ in range(12):
-    eng.step(torch.randint(0, n_act, (300, len(roles)), generator=gen, device='cuda', dtype=torch.int32))
+  for _ in range(8):
+    eng.step(torch.randint(0, n_act, (B, len(roles)), generator=gen, device='cuda', dtype=torch.int32))
   torch.cuda.synchronize()
-  print(name, 'ok', int(eng.rgb.sum()) % 1000, eng.launch_count())
+  snap = eng.save_state(); eng.load_state(snap)
+  print(name, 'ok', int(eng.rgb.sum()) % 1000, eng.launch_count(), int(eng.event_count.sum()), eng.render_plan())
   eng.close()

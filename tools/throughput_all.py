@@ -54,5 +54,5 @@ for name, players, B in CONFIGS:
                     'env_steps_per_sec': B / total_ms * 1e3, 'agent_steps_per_sec': B * players / total_ms * 1e3,
                     'step_kernel_ms': step_ms, 'render_kernel_ms': render_ms,
                     'render_GBps': rbytes * B / render_ms / 1e6, 'render_frac_of_peak': rbytes * B / render_ms / 1e6 / PEAK,
-                    'render_bytes_per_env': rbytes, 'whole_step_bytes_per_env': algo}), flush=True)
+                    'render_bytes_per_env': rbytes, 'whole_step_bytes_per_env': algo, 'render_plan': eng.render_plan()}), flush=True)
   eng.close()
