@@ -242,6 +242,25 @@ def run_b200(args, rank, world, local_rank):
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     e2e_s = float(tmax.item())
   e2e_value = world * B * n_e / e2e_s
+  # The same call with NULL image pointers: host actions in, rewards / discounts / step types / scalar observations
+  # out, images left in HBM for a GPU-resident consumer. Reported next to `e2e`, not instead of it.
+  scalars_out = {k: v for k, v in host_out.items() if k not in ('rgb', 'world_rgb')}
+  d2h_scalars = sum(t.numel() * t.element_size() for t in scalars_out.values())
+  n_s = max(n_e, min(K, 200))
+  host_actions_s = actions[:n_s].cpu().pin_memory()
+  eng.step_host(host_actions_s[0], scalars_out)
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  t0 = time.perf_counter()
+  for i in range(n_s):
+    eng.step_host(host_actions_s[i], scalars_out)
+  e2e_scalars_s = time.perf_counter() - t0
+  if world > 1:
+    tmax = torch.tensor([e2e_scalars_s], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    e2e_scalars_s = float(tmax.item())
+  e2e_scalars_value = world * B * n_s / e2e_scalars_s
 
   if rank == 0:
     line = {
@@ -260,6 +279,8 @@ def run_b200(args, rank, world, local_rank):
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'steps': n_e, 'api': 'mp_step_host (C ABI, pinned host buffers, all observations copied back)'},
+        'e2e_scalars_only': {'value': e2e_scalars_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h_scalars,
+                             'steps': n_s, 'api': 'mp_step_host with NULL image pointers (images stay in HBM)'},
         'roofline': {'bound': 'hbm', 'kernel': 'k_render', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': _traffic_per_launch(B), 'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': render_bytes * B, 'ms_per_launch': render_ms,
