@@ -105,6 +105,7 @@ struct mp_engine {
   void (*render_fn)(Tables, State, RenderPlan, uint32_t) = nullptr;
   uint64_t algo_bytes = 0, render_bytes = 0;
   std::vector<uint8_t> host_pair, host_sflags;  // kept for mp_debug_render_tables
+  int black_sprite = -1;
   std::vector<std::pair<void*, size_t>> state_spans;  // what mp_state_save / mp_state_load copy
   uint64_t state_bytes = 0;
 
@@ -487,9 +488,21 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   for (int i = 0; i < n_total; ++i) {
     bool bin = true;  // must hold for whatever sprite a viewer sees in its place
     for (int v = 0; v <= T.P; ++v) bin = bin && binary_alpha[smap[(size_t)v * n_total + i]];
-    sflags[i] = (uint8_t)((opq[i] ? 1 : 0) | (remapped[i] ? 2 : 0) | (bin ? 4 : 0));
+    bool invisible = true;  // every alpha 0, whatever a viewer sees in its place
+    for (int v = 0; v <= T.P && invisible; ++v) {
+      const int t = smap[(size_t)v * n_total + i];
+      for (int px = 0; px < 256 && invisible; ++px) invisible = img[(size_t)t * 1024 + px * 4 + 3] == 0;
+    }
+    sflags[i] = (uint8_t)((opq[i] ? 1 : 0) | (remapped[i] ? 2 : 0) | (bin ? 4 : 0) | (invisible ? 8 : 0));
   }
   E->host_pair = pair; E->host_sflags = sflags;
+  E->black_sprite = -1;  // an opaque, never remapped, all-black sprite stands in for cells with nothing to draw
+  for (int i = 0; i < n_total && E->black_sprite < 0; ++i) {
+    if (!opq[i] || remapped[i]) continue;
+    bool black = true;
+    for (int px = 0; px < 256 && black; ++px) { const uint8_t* q = &img[(size_t)i * 1024 + px * 4]; black = q[0] == 0 && q[1] == 0 && q[2] == 0; }
+    if (black) E->black_sprite = i;
+  }
   if ((rc = E->upload(smap, &T.sprite_map)) || (rc = E->upload(sflags, &T.sprite_opaque)) || (rc = E->upload(pair, &T.sprite_pair))) return rc;
   return MP_OK;
 }
@@ -561,6 +574,7 @@ int launch_render(mp_engine* E, cudaStream_t st) {
   R.prow_bytes = R.view_w * 24; R.wrow_bytes = T.W * 24;
   R.pitem_bytes = R.prow_bytes * 8; R.witem_bytes = R.wrow_bytes << R.wstrip_log2;
   R.h_oob = 0x8000 | (T.oob_sprite * 4); R.h_oov = 0x8000 | (T.oov_sprite * 4);
+  R.h_empty = E->black_sprite >= 0 ? (0x8000 | (E->black_sprite * 4)) : 0;
   E->render_fn<<<blocks, R.n_teams * R.team_threads, R.smem_bytes, st>>>(E->T, E->S, R, E->flags);
   ++E->launches;
   CUDA_TRY(cudaGetLastError());

@@ -61,6 +61,7 @@ struct RenderPlan {  // host-computed constants of the tiling
   int prow_bytes, wrow_bytes;            // one pixel row of a player image / of WORLD.RGB
   int pitem_bytes, witem_bytes;          // one strip
   int h_oob, h_oov;                      // fast-path headers of the OutOfBounds / OutOfView sprites
+  int h_empty;                           // header of a cell with nothing visible: fast path to an opaque black sprite, or 0
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,6 +125,7 @@ __device__ __forceinline__ uint32_t blend_px(uint32_t dst, uint32_t src) {
 // Record entry: bits 0-12 sprite * 4 + orientation, then the sprite's flag byte shifted by 13:
 // bit 13 = opaque, bit 14 = remapped for some viewer (look it up in the viewer's sprite map),
 // bit 15 = every alpha is 0 or 255 for every viewer (composited by selection instead of arithmetic).
+// (Flag bit 3, not kept in entries: every alpha is 0 -- such sprites never reach a record.)
 #define ENT_SHIFT 13
 #define ENT_VALUE 0x1fff
 #define ENT_OPAQUE 0x2000
@@ -174,8 +176,8 @@ __device__ __forceinline__ void cell_pass(const Tables& T, const RenderPlan& R, 
     uint32_t nz = 0, oq = 0;
 #pragma unroll
     for (int l = 0; l < LMAX; ++l) {
-      const uint32_t f = v[l] ? s_flags[(v[l] - 1) >> 2] : 0u;
-      nz |= (v[l] ? 1u : 0u) << l;
+      const uint32_t f = v[l] ? s_flags[(v[l] - 1) >> 2] : 8u;
+      nz |= ((f & 8u) ? 0u : 1u) << l;  // (bit 3: every alpha is 0 -- the piece is there but draws nothing)
       oq |= (f & 1u) << l;
     }
     oq &= ~1u;
@@ -200,7 +202,7 @@ __device__ __forceinline__ void cell_pass(const Tables& T, const RenderPlan& R, 
     }
     if (cur) r[1 + n++] = (uint16_t)((cur - 1) | (cf << ENT_SHIFT));
     if ((n == 1 && (cf & 1u)) || ((dbg & 256u) && cur)) r[0] = (uint16_t)(REC_FAST | (cur - 1));  // (bit 8: debug -- top sprite only)
-    else r[0] = (uint16_t)n;
+    else r[0] = n ? (uint16_t)n : (uint16_t)R.h_empty;  // nothing to draw: the black sprite if the atlas has one, else an empty record
   }
 }
 
