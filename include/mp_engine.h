@@ -69,7 +69,8 @@ typedef struct mp_buffers {
    * with 1-based player indices: 1 zap(source, target), 2 edible_consumed(player), 3 player_cleaned(player),
    * 4 claimed_resource(player), 5 destroyed_resource(player), 6 sanctioning(source, target),
    * 7 removal_due_to_sanctioning(source, target), 8 coin_consumed(player, 1 if the coin matched the player's type else 0;
-   * coins/components.lua:133-137). Rows of one step are in no particular order; event_count may
+   * coins/components.lua:133-137), 9 mining(player, ore type), 10 extraction(player, ore type),
+   * 11 extraction_pair(player_a, player_b | ore type << 8) (coop_mining/components.lua:203-234). Rows of one step are in no particular order; event_count may
    * exceed max_events, in which case only the first max_events rows were kept. */
   int32_t* events;          /* i32 [B][max_events][3] */
   int32_t* event_count;     /* i32 [B] */

@@ -72,10 +72,10 @@ enum MpbMeta {
   MPB_META_COUNT = 32
 };
 
-enum MpbFamily { MPB_FAMILY_CLEAN_UP = 1, MPB_FAMILY_COMMONS_HARVEST = 2, MPB_FAMILY_TERRITORY = 3, MPB_FAMILY_COINS = 4 };
+enum MpbFamily { MPB_FAMILY_CLEAN_UP = 1, MPB_FAMILY_COMMONS_HARVEST = 2, MPB_FAMILY_TERRITORY = 3, MPB_FAMILY_COINS = 4, MPB_FAMILY_COOP_MINING = 5 };
 
 /* Primitive action fields (columns of section "action_table"). */
-enum MpbActionField { MPB_ACT_MOVE = 0, MPB_ACT_TURN = 1, MPB_ACT_FIRE_ZAP = 2, MPB_ACT_FIRE_2 = 3 /* fireClean | fireClaim */ };
+enum MpbActionField { MPB_ACT_MOVE = 0, MPB_ACT_TURN = 1, MPB_ACT_FIRE_ZAP = 2 /* fireZap | mine */, MPB_ACT_FIRE_2 = 3 /* fireClean | fireClaim */ };
 
 /* Per-player scalar observation ids (section "scalar_obs", int32[N_SCALAR_OBS]). */
 enum MpbScalarObs { MPB_OBS_READY_TO_SHOOT = 0, MPB_OBS_NUM_OTHERS_WHO_CLEANED = 1, MPB_OBS_MISMATCHED_COIN_BY_PARTNER = 2 };
@@ -130,6 +130,11 @@ enum MpbComp {
   MPB_C_PLAYER_COIN_TYPE = 37, /* ip0 0 / 1: the player's coin type is the coin's liveStateA / liveStateB */
   MPB_C_COINS_ROLE = 38,       /* dp0..3 multipliers of the four Coin rewards (self match, self mismatch, other match, other mismatch) */
   MPB_C_PARTNER_TRACKER = 39,
+  MPB_C_FIXED_RATE_REGROW = 40, /* ip0 n live states (<= 4), ip1..4 live states, ip5 wait state; dp0..3 rates */
+  MPB_C_ORE = 41,              /* ip0 wait state, ip1 raw state, ip2 partial state, ip3 minNumMiners, ip4 miningWindow */
+  MPB_C_MINE_BEAM = 42,        /* ip0 cooldownTime, ip1 beamLength, ip2 beamRadius, ip3 'mine' hit id;
+                                  dp0..1 roleRewardForMining[role][1..2], dp2..3 roleRewardForExtracting[role][1..2] */
+  MPB_C_MINING_TRACKER = 43,
   MPB_C_COUNT
 };
 

@@ -8,7 +8,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ['engine.cu']
-HEADERS = ['common.cuh', 'render.cuh', 'step_clean_up.cuh', 'step_commons.cuh', 'step_territory.cuh', 'step_coins.cuh']
+HEADERS = ['common.cuh', 'render.cuh', 'step_clean_up.cuh', 'step_commons.cuh', 'step_territory.cuh', 'step_coins.cuh', 'step_mining.cuh']
 LIB_PATH = os.path.join(_HERE, 'libmpengine.so')
 
 NVCC_FLAGS = [

@@ -41,7 +41,8 @@ META = dict(FAMILY=0, W=1, H=2, L=3, P=4, SPRITE_SIZE=5, TOPOLOGY=6,
             VIEW_FORWARD=17, VIEW_BACKWARD=18, N_ACTIONS=19,
             N_ACTION_FIELDS=20, OOB_SPRITE=21, OOV_SPRITE=22, N_SCALAR_OBS=23)
 META_COUNT = 32
-FAMILY = {'clean_up': 1, 'commons_harvest': 2, 'territory': 3, 'coins': 4}
+FAMILY = {'clean_up': 1, 'commons_harvest': 2, 'territory': 3, 'coins': 4,
+          'coop_mining': 5}
 COMP = dict(StateManager=1, Transform=2, Appearance=3, BeamBlocker=4, Edible=5,
             AppleGrow=6, DirtTracker=7, DirtCleaning=8, Avatar=9, Zapper=10,
             ReadyToShootObservation=11, Cleaner=12, Taste=13,
@@ -53,9 +54,10 @@ COMP = dict(StateManager=1, Transform=2, Appearance=3, BeamBlocker=4, Edible=5,
             GraduatedSanctionsMarking=30, TerritoryTaste=31, Role=32,
             RoleBasedRewardTile=33, Coin=34, ChoiceCoinRegrow=35,
             GlobalCoinCollectionTracker=36, PlayerCoinType=37, CoinsRole=38,
-            PartnerTracker=39)
+            PartnerTracker=39, FixedRateRegrow=40, Ore=41, MineBeam=42,
+            MiningTracker=43)
 COMP_NI, COMP_ND = 16, 6
-ACTION_FIELDS = {'move': 0, 'turn': 1, 'fireZap': 2, 'fireClean': 3,
+ACTION_FIELDS = {'move': 0, 'turn': 1, 'fireZap': 2, 'mine': 2, 'fireClean': 3,
                  'fireClaim': 3}
 SCALAR_OBS = {'READY_TO_SHOOT': 0, 'NUM_OTHERS_WHO_CLEANED_THIS_STEP': 1,
               'MISMATCHED_COIN_COLLECTED_BY_PARTNER': 2}
@@ -65,7 +67,8 @@ BASE_LAYERS = ['logic', 'alternateLogic', 'background', 'lowerPhysical',
 _TASTE_ROLES = {'free': 0, 'cleaner': 1, 'consumer': 2}
 _TERRITORY_TASTE_ROLES = {'none': 0, 'rewarded_per_claim': 1, 'rewarded_per_claim_only': 2}
 _HIT_OF = {'Zapper': ('zapHit', 'beamZap', 'BeamZap'),
-           'Cleaner': ('cleanHit', 'beamClean', 'BeamClean')}
+           'Cleaner': ('cleanHit', 'beamClean', 'BeamClean'),
+           'MineBeam': ('mine', 'beamMine', 'beamMine')}  # coop_mining/components.lua:191-201
 
 
 # ---------------------------------------------------------------------------
@@ -355,6 +358,8 @@ class WorldModel:
           sp.add_color('BeamZap', kw.get('beamColor', (252, 252, 106)))
         elif c['component'] == 'Cleaner':
           sp.add_color('BeamClean', (99, 223, 242, 175))
+        elif c['component'] == 'MineBeam':
+          sp.add_color('beamMine', (255, 202, 202))
         elif c['component'] == 'ResourceClaimer':
           sp.add_color(f"claimBeamSprite_{int(kw['playerIndex'])}", kw['color'])
         elif c['component'] == 'Paintbrush':  # four explicit facings, noRotate (components.lua:374-385)
@@ -514,6 +519,26 @@ class WorldModel:
       elif name == 'Cleaner':
         ip[0], ip[1], ip[2] = int(kw['cooldownTime']), int(kw['beamLength']), int(kw['beamRadius'])
         ip[3] = hit_id('cleanHit')
+      elif name == 'MineBeam':  # coop_mining/components.lua:160-262
+        ip[0], ip[1], ip[2] = int(kw['cooldownTime']), int(kw['beamLength']), int(kw['beamRadius'])
+        ip[3] = hit_id('mine')
+        role = kw['agentRole']
+        mining, extracting = list(kw['roleRewardForMining'][role]), list(kw['roleRewardForExtracting'][role])
+        if len(mining) != 2 or len(extracting) != 2:
+          raise NotImplementedError('coop_mining with other than two ore types')
+        dp[0], dp[1], dp[2], dp[3] = (float(v) for v in mining + extracting)
+      elif name == 'Ore':  # coop_mining/components.lua:60-157
+        ip[0], ip[1], ip[2] = si(kw['waitState']), si(kw['rawState']), si(kw['partialState'])
+        ip[3], ip[4] = int(kw['minNumMiners']), int(kw['miningWindow'])
+      elif name == 'FixedRateRegrow':  # coop_mining/components.lua:25-58
+        live, rates = list(kw['liveStates']), list(kw['liveRates'])
+        if len(live) != len(rates) or len(live) > 4:
+          raise NotImplementedError('FixedRateRegrow with more than four live states')
+        ip[0] = len(live)
+        for i, st_name in enumerate(live):
+          ip[1 + i] = si(st_name)
+          dp[i] = float(rates[i])
+        ip[5] = si(kw['waitState'])
       elif name == 'Taste' and self.family != 'territory':
         ip[0] = _TASTE_ROLES[kw.get('role', 'free')]
         dp[0] = float(kw.get('rewardAmount', 1))
@@ -942,6 +967,59 @@ def _coins_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
   sections['co_coin'] = np.array([[c[0], c[1]] for c in coins], np.int32)
 
 
+def _mining_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
+  """SoA tables for the coop_mining step kernel (lua/levels/coop_mining/components.lua)."""
+  W = model.W
+  ores = []
+  for oid, ci in _objects_with(model, 'FixedRateRegrow'):
+    kid, x, y, orient, st = model.objects[oid]
+    ores.append((oid, y * W + x, kid, ci, st))
+  kid_o, ci_r = ores[0][2], ores[0][3]
+  if any(o[2] != kid_o for o in ores):
+    raise NotImplementedError('heterogeneous ore prefabs')
+  ko = model.kinds[kid_o]
+  ri, rd = model.comps_i[ci_r][1:], model.comps_d[ci_r]
+  ore_comps = [c for c in range(ko[2], ko[2] + ko[3]) if model.comps_i[c][0] == COMP['Ore']]
+  if ri[0] != 2 or len(ore_comps) != 2:
+    raise NotImplementedError('coop_mining needs two ore types (two Ore components, two live states)')
+  wait = ri[5]
+  if any(o[4] != wait for o in ores):
+    raise NotImplementedError('ores that do not start in the wait state')
+  # which Ore component owns which live state; "single" ore: one miner extracts, "joint" ore: two miners within the window
+  by_raw = {model.comps_i[c][2]: model.comps_i[c][1:] for c in ore_comps}
+  single, joint = by_raw[ri[1]], by_raw[ri[2]]
+  if single[3] != 1 or joint[3] != 2 or single[0] != wait or joint[0] != wait or single[2] != single[1]:
+    raise NotImplementedError('ore types other than (1 miner, no partial state) and (2 miners, partial state)')
+  st = lambda i: model.states[ko[0] + i]
+  layers = {st(i)[0] for i in (wait, single[1], joint[1], joint[2])}
+  if len(layers) != 1:
+    raise NotImplementedError('ore states on different layers')
+  beams = []
+  for oid in model.avatar_objs:
+    k = model.kinds[model.objects[oid][0]]
+    ci = [c for c in range(k[2], k[2] + k[3]) if model.comps_i[c][0] == COMP['MineBeam']][0]
+    beams.append((model.comps_i[ci][1:], model.comps_d[ci]))
+  if any(b != beams[0] for b in beams[1:]):
+    raise NotImplementedError('per-avatar MineBeam parameters')
+  bi, bd = beams[0]
+  if bi[2] != 0:
+    raise NotImplementedError('mine beams with a radius')
+  scene_k = model.kinds[model.objects[0][0]]
+  end = [c for c in range(scene_k[2], scene_k[2] + scene_k[3])
+         if model.comps_i[c][0] == COMP['StochasticIntervalEpisodeEnding']][0]
+  ei, ed = model.comps_i[end][1:], model.comps_d[end]
+  hits = {h[0]: (model.layers.index(h[1]), model.sprites.index(h[2])) for h in model.hits}
+  ip = np.zeros(48, np.int32)
+  dp = np.zeros(16, np.float64)
+  ip[0:8] = [len(ores), st(wait)[0], st(wait)[1], st(single[1])[1], st(joint[1])[1], st(joint[2])[1], joint[4], bi[0]]
+  ip[8:14] = [bi[1], hits['mine'][0], hits['mine'][1], ei[0], ei[1], bi[3]]
+  dp[0:3] = [rd[0], rd[1], ed[0]]
+  dp[4:8] = bd[0:4]
+  sections['cm_ip'] = ip
+  sections['cm_dp'] = dp
+  sections['cm_ore'] = np.array([[o[0], o[1]] for o in ores], np.int32)
+
+
 def _territory_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
   """SoA tables for the territory step kernel."""
   W, P = model.W, model.num_players
@@ -1115,6 +1193,8 @@ def compile_settings(settings: Mapping[str, Any],
     _territory_tables(model, sections)
   elif model.family == 'coins':
     _coins_tables(model, sections)
+  elif model.family == 'coop_mining':
+    _mining_tables(model, sections)
   info = dict(
       level=model.level, family=model.family, layers=model.layers,
       sprites=model.sprites.names, groups=model.groups,

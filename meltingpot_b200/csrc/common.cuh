@@ -98,6 +98,11 @@ struct Tables {
   double coin_reward[2][4];    // per collecting player: self match, self mismatch, other match, other mismatch
   double coin_rate;            // ChoiceCoinRegrow regrowRate
   int coin_terminate, coin_terminate_n;
+  // coop_mining family (step_mining.cuh); ores reuse ch_apple / apple_of_cell / apple_layer, the beam reuses zap_*
+  int ore_sprite[4];           // wait, single-miner raw, two-miner raw, two-miner partial
+  int mine_window, mine_length;
+  double mine_rate[2];         // FixedRateRegrow liveRates
+  double mine_reward[2], extract_reward[2];  // per ore type (1 miner, 2 miners)
 };
 
 struct State {
@@ -131,7 +136,9 @@ struct State {
 // the order of oracle/mp_oracle.c; player indices are 1-based as in Lua.
 #define MP_MAX_EVENTS 64
 enum { EV_ZAP = 1, EV_EDIBLE_CONSUMED = 2, EV_PLAYER_CLEANED = 3, EV_CLAIMED_RESOURCE = 4, EV_DESTROYED_RESOURCE = 5,
-       EV_SANCTIONING = 6, EV_REMOVAL = 7, EV_COIN_CONSUMED = 8 /* a = player, b = 1 match / 0 mismatch */ };
+       EV_SANCTIONING = 6, EV_REMOVAL = 7, EV_COIN_CONSUMED = 8 /* a = player, b = 1 match / 0 mismatch */,
+       EV_MINING = 9 /* a = player, b = ore type */, EV_EXTRACTION = 10 /* a = player, b = ore type */,
+       EV_EXTRACTION_PAIR = 11 /* a = player_a, b = player_b | ore type << 8 */ };
 
 // Called by the one lane that owns the event. Lanes append concurrently, so the order within a
 // step is unspecified (hosts sort); the per-env counter is zeroed at kernel entry.

@@ -18,6 +18,7 @@
 #include "step_commons.cuh"
 #include "step_territory.cuh"
 #include "step_coins.cuh"
+#include "step_mining.cuh"
 
 namespace {
 
@@ -162,7 +163,7 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
   if (T.topology == 1 && (T.view_l + T.view_r + 1 > T.W || T.view_f + T.view_b + 1 > T.H || T.view_l + T.view_r + 1 > T.H || T.view_f + T.view_b + 1 > T.W))
     return fail(MP_E_UNSUPPORTED, "TORUS map smaller than the view window");
   for (int k = 0; k < T.n_scalar; ++k) T.scalar_obs[k] = scalar_obs.data[k];
-  if (E->family != MPB_FAMILY_CLEAN_UP && E->family != MPB_FAMILY_COMMONS_HARVEST && E->family != MPB_FAMILY_TERRITORY && E->family != MPB_FAMILY_COINS) return fail(MP_E_UNSUPPORTED, "substrate family %d has no CUDA state-transition kernel yet", E->family);
+  if (E->family != MPB_FAMILY_CLEAN_UP && E->family != MPB_FAMILY_COMMONS_HARVEST && E->family != MPB_FAMILY_TERRITORY && E->family != MPB_FAMILY_COINS && E->family != MPB_FAMILY_COOP_MINING) return fail(MP_E_UNSUPPORTED, "substrate family %d has no CUDA state-transition kernel yet", E->family);
 
   // ---- avatars ---------------------------------------------------------------------------------
   T.avatar_layer = av_table.data[2];
@@ -277,6 +278,26 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
     T.zap_layer = 0; T.zap_cooldown = 1;
     v_apple.resize((size_t)T.nA * 4);
     for (int k = 0; k < T.nA; ++k) { v_apple[k * 4] = co_coin.data[k * 2]; v_apple[k * 4 + 1] = co_coin.data[k * 2 + 1]; v_apple[k * 4 + 2] = 0; v_apple[k * 4 + 3] = -1; }
+    if ((rc = E->upload(v_apple, &T.ch_apple))) return rc;
+  }
+  else if (E->family == MPB_FAMILY_COOP_MINING) {
+    Section<int32_t> cm_ip, cm_ore;
+    Section<double> cm_dp;
+    NEED(cm_ip, MPB_I32) NEED(cm_dp, MPB_F64) NEED(cm_ore, MPB_I32)
+    const int32_t* ip = cm_ip.data; const double* dp = cm_dp.data;
+    T.nA = ip[0]; T.apple_layer = ip[1];
+    for (int i = 0; i < 4; ++i) T.ore_sprite[i] = ip[2 + i];
+    T.mine_window = ip[6]; T.zap_cooldown = ip[7]; T.mine_length = ip[8]; T.zap_layer = ip[9]; T.zap_sprite = ip[10];
+    T.end_min_frames = ip[11]; T.end_interval = ip[12]; T.zap_hit = ip[13];
+    if (T.P > 8) return fail(MP_E_UNSUPPORTED, "coop_mining with %d players (max 8: miners are kept as a bit mask)", T.P);
+    if (T.nA > 2048) return fail(MP_E_UNSUPPORTED, "%d ores (max 2048)", T.nA);
+    if (T.zap_cooldown < 1 || T.mine_window < 1 || T.mine_window > 255 || T.mine_length < 1) return fail(MP_E_UNSUPPORTED, "MineBeam / Ore parameters out of range");
+    if (T.end_interval < 1) return fail(MP_E_INVALID, "episode interval < 1");
+    if (T.zap_hit < 0 || T.zap_hit > 7) return fail(MP_E_UNSUPPORTED, "mine hit id %d", T.zap_hit);
+    T.mine_rate[0] = dp[0]; T.mine_rate[1] = dp[1]; T.end_prob = dp[2];
+    T.mine_reward[0] = dp[4]; T.mine_reward[1] = dp[5]; T.extract_reward[0] = dp[6]; T.extract_reward[1] = dp[7];
+    v_apple.resize((size_t)T.nA * 4);
+    for (int k = 0; k < T.nA; ++k) { v_apple[k * 4] = cm_ore.data[k * 2]; v_apple[k * 4 + 1] = cm_ore.data[k * 2 + 1]; v_apple[k * 4 + 2] = 0; v_apple[k * 4 + 3] = -1; }
     if ((rc = E->upload(v_apple, &T.ch_apple))) return rc;
   }
   else {  // MPB_FAMILY_TERRITORY
@@ -558,6 +579,7 @@ int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int 
   if (E->family == MPB_FAMILY_CLEAN_UP) k_step_clean_up<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
   else if (E->family == MPB_FAMILY_COMMONS_HARVEST) k_step_commons<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
   else if (E->family == MPB_FAMILY_COINS) k_step_coins<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
+  else if (E->family == MPB_FAMILY_COOP_MINING) k_step_mining<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
   else k_step_territory<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
@@ -671,6 +693,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_commons, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_territory, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_coins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_mining, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
   if (ce != cudaSuccess) { mp_destroy(E); return fail(MP_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)); }
   mp_buffers& bf = E->buffers;
   bf.num_envs = num_envs; bf.num_players = T.P; bf.rgb_h = E->R.view_h * 8; bf.rgb_w = E->R.view_w * 8;

@@ -54,6 +54,16 @@ __device__ void coins_reset(const Tables& T, const State& S, int b, int lane, Wa
     S.packed[(size_t)b * (T.P + 2) + lane] = 0.0;
     for (int k = 0; k < T.n_scalar; ++k) S.scalar_obs[((size_t)k * S.B + b) * T.P + lane] = 0.0;
   }
+  // api:start ends with one grid:update (api_factory.lua:101): the ChoiceCoinRegrow updaters already fire at frame 0.
+  // (Spawn points are not coin cells, so no avatar can be standing on a coin that appears now.)
+  for (int k = lane; k < T.nA; k += 32) {
+    uint4 w = philox4x32_10(0u, (uint32_t)episode, (uint32_t)T.ch_apple[k * 4], RS_OBJECT, k0, k1);
+    if (u01(w.x, w.y) < T.coin_rate) {
+      const int type = (int)pick(w.z, 2u);
+      S.apple[(size_t)b * T.nA_pad + k] = (uint8_t)(1 + type);
+      grid[(size_t)T.apple_layer * T.cells_pad + T.ch_apple[k * 4 + 1]] = cell_value(T.coin_sprite[type], 0);
+    }
+  }
   if (lane == 0) {
     env[ENV_STEP] = 0; env[ENV_EPISODE] = episode; env[ENV_DONE] = 0; env[ENV_DIRT] = 0;
     env[ENV_CLEANED] = 0; env[ENV_ATE] = 0; env[ENV_BEAM] = 0;

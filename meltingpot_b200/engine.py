@@ -94,10 +94,12 @@ def load_library() -> ctypes.CDLL:
 
 
 EVENT_NAMES = {1: 'zap', 2: 'edible_consumed', 3: 'player_cleaned', 4: 'claimed_resource',
-               5: 'destroyed_resource', 6: 'sanctioning', 7: 'removal_due_to_sanctioning', 8: 'coin_consumed'}
+               5: 'destroyed_resource', 6: 'sanctioning', 7: 'removal_due_to_sanctioning', 8: 'coin_consumed',
+               9: 'mining', 10: 'extraction', 11: 'extraction_pair'}
 # argument names of each event's dict payload (second one unused for single-argument events)
 EVENT_FIELDS = {1: ('source', 'target'), 2: ('player_index',), 3: ('player_index',), 4: ('player_index',),
-                5: ('player_index',), 6: ('source', 'target'), 7: ('source', 'target'), 8: ('player_index', 'matched')}
+                5: ('player_index',), 6: ('source', 'target'), 7: ('source', 'target'), 8: ('player_index', 'matched'),
+                9: ('player', 'ore_type'), 10: ('player', 'ore_type'), 11: ('player_a', 'player_b_and_ore_type')}
 
 
 class EngineError(RuntimeError):

@@ -17,6 +17,7 @@ PRECOMPILED = {
     'commons_harvest__closed': (7,),
     'commons_harvest__partnership': (7,),
     'coins': (2,),
+    'coop_mining': (6,),
 }
 
 # Substrates with build-time randomness: 'choice' prefabs drawn per env instance (prefab_utils.lua:63-65), or

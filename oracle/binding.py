@@ -84,7 +84,8 @@ def _ptr(arr, ctype):
 
 
 EVENT_NAMES = {1: 'zap', 2: 'edible_consumed', 3: 'player_cleaned', 4: 'claimed_resource',
-               5: 'destroyed_resource', 6: 'sanctioning', 7: 'removal_due_to_sanctioning', 8: 'coin_consumed'}
+               5: 'destroyed_resource', 6: 'sanctioning', 7: 'removal_due_to_sanctioning', 8: 'coin_consumed',
+               9: 'mining', 10: 'extraction', 11: 'extraction_pair'}
 
 
 class OracleEnv:

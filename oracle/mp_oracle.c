@@ -86,19 +86,24 @@ typedef struct {
   int level, time_not_initial, marking_avatar;       /* GraduatedSanctionsMarking */
   int partner_match, partner_mismatch;               /* PartnerTracker (coins) */
   int coins_cumulative;                              /* GlobalCoinCollectionTracker.cumulativeCoinsCollected(player) */
+  int ore_miners[2], ore_cd[2];                      /* Ore._miners (bit per player), Ore._miningCountdown -- one pair per Ore component */
+  int mine_cool;                                     /* MineBeam._coolingTimer */
 } Obj;
 
 enum { ACT_SET_STATE, ACT_TURN, ACT_MOVE_REL, ACT_TELEPORT_GROUP, ACT_BEAM, ACT_TELEPORT, ACT_SET_ORIENT };
 typedef struct { int type, obj, a, b, c; } Action;
 
 enum { EV_ZAP = 1, EV_EDIBLE_CONSUMED = 2, EV_PLAYER_CLEANED = 3, EV_CLAIMED_RESOURCE = 4, EV_DESTROYED_RESOURCE = 5, EV_SANCTIONING = 6, EV_REMOVAL = 7,
-       EV_COIN_CONSUMED = 8 /* a = player, b = 1 match / 0 mismatch */ };
+       EV_COIN_CONSUMED = 8 /* a = player, b = 1 match / 0 mismatch */,
+       EV_MINING = 9 /* a = player, b = ore type */, EV_EXTRACTION = 10 /* a = player, b = ore type */,
+       EV_EXTRACTION_PAIR = 11 /* a = player_a, b = player_b | ore type << 8 */ };
 typedef struct { int type, a, b; } Event;
 
 enum { /* updater function ids */
   UF_AVATAR_MOVE, UF_ZAP, UF_RESPAWN, UF_CLEAN, UF_CLEANER_RESET, UF_TASTE_RESET, UF_NONSELF_GET,
   UF_NONSELF_RESET, UF_GLOBAL_RESET, UF_EPISODE_END, UF_ANIMATION, UF_SPROUT,
-  UF_PAINTBRUSH, UF_CLAIM, UF_PROVIDE_REWARDS, UF_RELEASE_CLAIM, UF_MARKING_RECOVERY, UF_COIN_REGROW
+  UF_PAINTBRUSH, UF_CLAIM, UF_PROVIDE_REWARDS, UF_RELEASE_CLAIM, UF_MARKING_RECOVERY, UF_COIN_REGROW,
+  UF_ORE_REGROW_0, UF_ORE_REGROW_1
 };
 typedef struct { int priority, comp_type, fn, seq; } Updater;
 
@@ -327,6 +332,31 @@ static int on_hit(OrEnv* e, int target, int shooter, int hit) {
           blocked = 1;
         }
         break;
+      case MPB_C_ORE: { /* Ore:onHit -- coop_mining/components.lua:118-150 (an ore object carries one Ore component per ore type) */
+        const CompDef* mb = find_comp(e, sh, MPB_C_MINE_BEAM);
+        if (!mb || hit != mb->ip[3] || (t->state != c->ip[1] && t->state != c->ip[2])) break;
+        int k = 0; /* which of the object's Ore components this is */
+        for (int j = 0; j < i; ++j) if (e->comps[kind_of(e, t)->comp0 + j].type == MPB_C_ORE) ++k;
+        const int me = find_comp(e, sh, MPB_C_AVATAR)->ip[0], type = c->ip[3];
+        t->ore_cd[k] = c->ip[4]; t->ore_miners[k] |= 1 << me;             /* Ore:addMiner :110-114 */
+        enqueue(e, ACT_SET_STATE, target, c->ip[2], 0, 0);
+        avatar_add_reward(e, sh, mb->dp[type - 1]);                        /* MineBeam:processRoleMineEvent :203-212 */
+        add_event(e, EV_MINING, me + 1, type);
+        int count = 0;
+        for (int p = 0; p < e->P; ++p) count += (t->ore_miners[k] >> p) & 1;
+        if (count == c->ip[3]) {
+          for (int p = 0; p < e->P; ++p) if ((t->ore_miners[k] >> p) & 1) {
+            Obj* av = &e->obj[e->avatar_obj[p]];
+            avatar_add_reward(e, av, find_comp(e, av, MPB_C_MINE_BEAM)->dp[2 + type - 1]); /* processRoleExtractEvent :214-224 */
+            add_event(e, EV_EXTRACTION, p + 1, type);
+            for (int q = 0; q < e->P; ++q) if (q != p && ((t->ore_miners[k] >> q) & 1)) add_event(e, EV_EXTRACTION_PAIR, p + 1, (q + 1) | (type << 8));
+          }
+          t->ore_miners[k] = 0; t->ore_cd[k] = 0;                          /* Ore:reset :96-103 */
+          if (t->state != c->ip[0]) enqueue(e, ACT_SET_STATE, target, c->ip[1], 0, 0);
+          enqueue(e, ACT_SET_STATE, target, c->ip[0], 0, 0);
+        }
+        blocked = 1;
+      } break;
       case MPB_C_ALL_BEAM_BLOCKER: blocked = 1; break; /* territory/components.lua:46-49 */
       case MPB_C_RESOURCE: if (resource_on_hit(e, target, shooter, hit, c)) blocked = 1; break;
       case MPB_C_GRADUATED_SANCTIONS_MARKING: marking_on_hit(e, target, shooter, hit, c); break; /* never blocks */
@@ -671,6 +701,15 @@ static void run_updater(OrEnv* e, const Updater* u, int oi) {
       uint32_t w[4]; rng(e, RS_OBJECT, oi, w);
       if (u01(w[0], w[1]) < c->dp[0]) enqueue(e, ACT_SET_STATE, oi, c->ip[pick(w[2], 2u)], 0, 0); /* random:choice(liveStates) */
     } break;
+    case UF_ORE_REGROW_0: case UF_ORE_REGROW_1: { /* FixedRateRegrow (coop_mining/components.lua:41-57): priority 200, one updater per live state */
+      const int i = u->fn - UF_ORE_REGROW_0;
+      if (o->state != c->ip[5] || i >= c->ip[0]) break;
+      uint32_t w[4]; rng(e, RS_OBJECT, oi, w);
+      if (!(u01(w[2 * i], w[2 * i + 1]) < c->dp[i])) break;
+      const Obj* a0 = &e->obj[e->avatar_obj[0]]; /* transform:queryPosition('upperPhysical'): the avatars' layer */
+      const int layer = state_def(e, a0, find_comp(e, a0, MPB_C_AVATAR)->ip[1])->layer;
+      if (e->grid[layer * e->W * e->H + cell_of(e, o->x, o->y)] == 0) enqueue(e, ACT_SET_STATE, oi, c->ip[1 + i], 0, 0);
+    } break;
     case UF_ANIMATION: { /* component_library.lua:1070-1094: one updater per state, startFrame */
       if (age < c->ip[9]) break;
       int n = c->ip[0];
@@ -709,6 +748,7 @@ static void build_updaters(OrEnv* e) {
         case MPB_C_ANIMATION: add_updater(e, 100, MPB_C_ANIMATION, UF_ANIMATION); break;
         case MPB_C_DENSITY_REGROW: add_updater(e, 10, MPB_C_DENSITY_REGROW, UF_SPROUT); break;
         case MPB_C_CHOICE_COIN_REGROW: add_updater(e, 100, MPB_C_CHOICE_COIN_REGROW, UF_COIN_REGROW); break; /* default priority (updater_registry.lua:47) */
+        case MPB_C_FIXED_RATE_REGROW: add_updater(e, 200, MPB_C_FIXED_RATE_REGROW, UF_ORE_REGROW_0); add_updater(e, 200, MPB_C_FIXED_RATE_REGROW, UF_ORE_REGROW_1); break;
         case MPB_C_PAINTBRUSH: add_updater(e, 130, MPB_C_PAINTBRUSH, UF_PAINTBRUSH); break;
         case MPB_C_RESOURCE_CLAIMER: add_updater(e, 100, MPB_C_RESOURCE_CLAIMER, UF_CLAIM); break;
         case MPB_C_RESOURCE: add_updater(e, 100, MPB_C_RESOURCE, UF_PROVIDE_REWARDS); add_updater(e, 2, MPB_C_RESOURCE, UF_RELEASE_CLAIM); break;
@@ -775,6 +815,19 @@ static void simulation_update(OrEnv* e) {
           e->spawner_t++;
         } break;
         case MPB_C_STOCHASTIC_INTERVAL_EPISODE_ENDING: e->ending_t++; break; /* component_library.lua:946-948 */
+        case MPB_C_ORE: { /* Ore:update -- coop_mining/components.lua:104-109 */
+          int kk = 0; /* which of the object's Ore components this is */
+          for (int j = 0; j < i; ++j) if (e->comps[k->comp0 + j].type == MPB_C_ORE) ++kk;
+          o->ore_cd[kk] -= 1;
+          if (o->ore_cd[kk] == 0) { /* Ore:reset :96-103 */
+            o->ore_miners[kk] = 0;
+            if (o->state != c->ip[0]) enqueue(e, ACT_SET_STATE, oi, c->ip[1], 0, 0);
+          }
+        } break;
+        case MPB_C_MINE_BEAM: { /* MineBeam:update -- coop_mining/components.lua:236-252 */
+          if (o->mine_cool > 0) o->mine_cool--;
+          if (o->act[MPB_ACT_FIRE_ZAP] == 1 && o->mine_cool == 0) { o->mine_cool = c->ip[0]; enqueue(e, ACT_BEAM, oi, c->ip[3], c->ip[1], c->ip[2]); }
+        } break;
         case MPB_C_AVATAR: { /* Avatar:update -- avatar_library.lua:334-354 */
           if (o->freeze == 1) o->movement_allowed = 1;
           o->freeze = o->freeze > 0 ? o->freeze - 1 : 0;
@@ -1044,7 +1097,9 @@ void oracle_get_scalar_obs(const OrEnv* e, double* out) {
       double v = 0.0;
       if (e->scalar_obs[k] == MPB_OBS_READY_TO_SHOOT) { /* Zapper:readyToShoot -- avatar_library.lua:737-744 */
         const CompDef* z = find_comp(e, o, MPB_C_ZAPPER);
-        if (avatar_is_alive(e, o)) v = fmax(1.0 - (double)o->zap_cool / (double)z->ip[0], 0.0);
+        const CompDef* mb = find_comp(e, o, MPB_C_MINE_BEAM);
+        if (mb) v = 1.0 - (double)o->mine_cool / (double)mb->ip[0]; /* MineBeam:readyToShoot -- coop_mining/components.lua:186-189 */
+        else if (avatar_is_alive(e, o)) v = fmax(1.0 - (double)o->zap_cool / (double)z->ip[0], 0.0);
       } else if (e->scalar_obs[k] == MPB_OBS_NUM_OTHERS_WHO_CLEANED) v = (double)o->num_others_cleaned;
       else if (e->scalar_obs[k] == MPB_OBS_MISMATCHED_COIN_BY_PARTNER) v = (double)o->partner_mismatch;
       out[p * e->n_scalar + k] = v;

@@ -77,3 +77,9 @@ def commons_partnership_blob():
 def coins_blob():
   from meltingpot_b200 import substrates
   return substrates.load_blob('coins', ('default',) * 2)
+
+
+@pytest.fixture(scope='session')
+def coop_mining_blob():
+  from meltingpot_b200 import substrates
+  return substrates.load_blob('coop_mining', ('default',) * 6)

@@ -187,5 +187,17 @@ def test_events_reach_the_dm_env_api(clean_up_blob):
 
 def test_coins_random_rollout(coins_blob, oracle):
   # the eighth substrate of the sweep; two players, no beams, coin_consumed events.
-  stats = parity.compare_rollout(coins_blob, oracle, num_envs=24, steps=900, seed=31, pixels_every=4)
+  # (64 envs: a coin appears during the start update of an episode in about one env in twenty)
+  stats = parity.compare_rollout(coins_blob, oracle, num_envs=64, steps=700, seed=31, pixels_every=7)
   assert stats['events'] > 30
+
+
+def _mine_heavy(t, B, P, A, rng):
+  probs = np.array([0.05, 0.15, 0.1, 0.1, 0.1, 0.1, 0.1, 0.3])
+  return rng.choice(A, size=(B, P), p=probs)
+
+
+def test_coop_mining_rollout(coop_mining_blob, oracle):
+  # ninth substrate; beams fired from component updates, two Ore components per ore object.
+  stats = parity.compare_rollout(coop_mining_blob, oracle, num_envs=16, steps=1300, seed=41, actions_fn=_mine_heavy, pixels_every=5)
+  assert stats['events'] > 200 and stats['rewards'] > 50

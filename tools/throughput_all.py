@@ -19,6 +19,7 @@ CONFIGS = [
     ('commons_harvest__closed', 7, 4096),
     ('commons_harvest__partnership', 7, 4096),
     ('coins', 2, 8192),
+    ('coop_mining', 6, 4096),
 ]
 PEAK = 6561.6
 if os.path.exists('MEASURED_PEAKS.json'):
