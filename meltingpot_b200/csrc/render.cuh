@@ -248,6 +248,9 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
   int team = 0;
 #pragma unroll
   for (int k = 1; k < RENDER_MAX_TEAMS; ++k) team += tid >= k * R.team_threads;
+  // `team` feeds every shared-memory base below; pinned so that the compiler keeps it in a register instead of
+  // re-deriving it from threadIdx inside the strip loop (measured: 1-2 % of the kernel)
+  asm volatile("" : "+r"(team));
   const int ttid = tid - team * R.team_threads;
   const int lane = tid & 31, twarp = ttid >> 5;
   uint8_t* s_team = smem + R.off_team0 + team * R.team_stride;
