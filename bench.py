@@ -137,7 +137,7 @@ def run_reference(args, rank, world):
       'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'agent_steps_per_sec': value * 7,
   }
-  print(json.dumps(line), flush=True)
+  _emit(line)
 
 
 def run_b200(args, rank, world, local_rank):
@@ -289,10 +289,20 @@ def run_b200(args, rank, world, local_rank):
     }
     if not args.no_cpu_baseline and world == 1:
       line['cpu_baseline'] = cpu_baseline(blob)
-    print(json.dumps(line), flush=True)
+    _emit(line)
   eng.close()
   if world > 1:
     dist.destroy_process_group()
+
+
+_STDOUT_FD = []  # the real stdout, saved by main() while fd 1 points at stderr
+
+
+def _emit(line):
+  sys.stdout.flush()
+  if _STDOUT_FD:
+    os.dup2(_STDOUT_FD[0], 1)
+  print(json.dumps(line), flush=True)
 
 
 def main():
@@ -308,6 +318,11 @@ def main():
   rank = int(os.environ.get('RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  # Exactly one JSON line on stdout: native libraries (NCCL prints its version banner there) write to the stdout
+  # file descriptor, so everything but the final line is sent to stderr.
+  sys.stdout.flush()
+  _STDOUT_FD.append(os.dup(1))
+  os.dup2(2, 1)
   if args.impl == 'reference':
     run_reference(args, rank, world)
   else:
