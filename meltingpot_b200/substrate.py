@@ -35,7 +35,8 @@ from ml_collections import config_dict  # noqa: E402  pylint: disable=g-import-n
 
 SUBSTRATES = frozenset(substrate_blobs.PRECOMPILED)
 _COLLECTIVE_REWARD_OBS = 'COLLECTIVE_REWARD'
-_SCALAR_NAMES = {0: 'READY_TO_SHOOT', 1: 'NUM_OTHERS_WHO_CLEANED_THIS_STEP'}
+_SCALAR_NAMES = {0: 'READY_TO_SHOOT', 1: 'NUM_OTHERS_WHO_CLEANED_THIS_STEP',
+                 2: 'MISMATCHED_COIN_COLLECTED_BY_PARTNER'}  # include/mpb_format.h MpbScalarObs
 _MAX_SEED = 2**32 - 1
 
 

@@ -124,3 +124,13 @@ def test_role_tile_is_inert_for_default_roles_and_refused_when_it_would_pay(orac
     assert (r >= 0).all()  # the -10 tile never fires for role 'none'
     total += r.sum()
   assert total > 0
+
+
+def test_every_scalar_observation_id_has_a_name():
+  # (a blob whose scalar observation the Python layer cannot name fails only when an env is built -- on a GPU)
+  for name, counts in substrates.PRECOMPILED.items():
+    for players in counts:
+      sec = mpb.unpack(substrates.load_blob(name, ('default',) * players))
+      info = json.loads(mpb.section_text(sec, 'info_json'))
+      named = [substrate._SCALAR_NAMES[int(k)] for k in sec['scalar_obs']]  # pylint: disable=protected-access
+      assert named == [n for n in info['individual_observation_names'] if n != 'RGB']
