@@ -56,4 +56,16 @@ for name, players, B in CONFIGS:
                     'step_kernel_ms': step_ms, 'render_kernel_ms': render_ms,
                     'render_GBps': rbytes * B / render_ms / 1e6, 'render_frac_of_peak': rbytes * B / render_ms / 1e6 / PEAK,
                     'render_bytes_per_env': rbytes, 'whole_step_bytes_per_env': algo, 'render_plan': eng.render_plan()}), flush=True)
+  if name == 'clean_up':  # secondary line of SURVEY.md section 8d config 2: WORLD.RGB off
+    eng.set_flags(engine.MP_FLAG_RENDER_PLAYERS)
+    for t in range(W):
+      eng.step(acts[t])
+    torch.cuda.synchronize()
+    e0.record()
+    for t in range(W, W + K):
+      eng.step(acts[t])
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    print(json.dumps({'substrate': name, 'players': players, 'envs': B, 'world_rgb': False, 'ms_per_step': ms,
+                      'env_steps_per_sec': B / ms * 1e3, 'agent_steps_per_sec': B * players / ms * 1e3}), flush=True)
   eng.close()
