@@ -52,7 +52,7 @@ struct RenderPlan {  // host-computed constants of the tiling
   int off_atlas, off_pair, off_map, off_team0, team_stride;
   int toff_grid, toff_rec, toff_stage;  // within a team's region
   int wstrip_log2;                      // log2 of the pixel rows per WORLD.RGB strip (1 or 2)
-  int stage_bytes;                      // warp-private staging buffer: two slots, each one player cell-row or half a world cell-row
+  int stage_bytes;                      // warp-private staging buffer: RENDER_SLOTS slots, each one player cell-row or one WORLD.RGB strip
   int smem_bytes;
   int team_threads;                     // threads per team (multiple of 32, <= TEAM_THREADS)
   int n_teams;                          // teams per CTA (2..RENDER_MAX_TEAMS); n_teams * team_threads <= 1024
@@ -231,7 +231,7 @@ struct ViewerInfo {  // per player, refreshed once per env
 // Work decomposition: an env is rendered by one team; after the per-cell pass its warps pull
 // strip items from a shared counter -- one row of view cells (8 pixel rows) of a player image, or
 // a half / quarter cell row (4 / 2 pixel rows) of WORLD.RGB -- compose them into a warp-private staging slot and
-// hand the slot to the TMA store engine. Three team barriers per env; everything else is warp-local.
+// hand the slot to the TMA store engine. Two team barriers per env; everything else is warp-local.
 // Each lane handles NC cells per strip with the loads of all NC cells issued before any is packed.
 template <int NCP, int NCW>
 __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, State S, RenderPlan R, uint32_t flags) {
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
   uint8_t* s_team = smem + R.off_team0 + team * R.team_stride;
   uint16_t* s_grid = reinterpret_cast<uint16_t*>(s_team + R.toff_grid);
   uint16_t* s_rec = reinterpret_cast<uint16_t*>(s_team + R.toff_rec);
-  uint8_t* s_stage = s_team + R.toff_stage + twarp * R.stage_bytes;  // warp-private, two slots
+  uint8_t* s_stage = s_team + R.toff_stage + twarp * R.stage_bytes;  // warp-private
   ViewerInfo* s_view = s_view_all[team];
   uint64_t* gbar = &bar[1 + team];
 

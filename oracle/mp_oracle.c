@@ -10,7 +10,7 @@
  * What IS pinned: Philox4x32-10 known answers (Random123), and the behaviours the reference's
  * Lua tests state (game_object_test.lua:252-411) -- see tests/test_oracle_semantics.py.
  *
- * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this library.
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU legs (cpu_baseline, --impl reference) may load this library.
  * The product (meltingpot_b200/csrc) shares no code with it except include/mpb_format.h
  * (the blob layout).
  *
