@@ -190,6 +190,7 @@ __device__ void mining_step(const Tables& T, const State& S, int b, int lane, co
             emit_event(S, b, EV_MINING, src + 1, 1);
             emit_event(S, b, EV_EXTRACTION, src + 1, 1);
           }
+          __syncwarp();  // every lane has read the ore's state byte before lane 0 rewrites it
           if (lane == 0) s_state[k] = (uint8_t)((s_state[k] & ~(3 << 4)) | (2 << 4));
         } else {
           const unsigned miners = s_miners[k] | (1u << src);  // Ore:addMiner (:110-114)

@@ -9,8 +9,11 @@ import torch
 from meltingpot_b200 import engine, substrates
 
 CASES = (('clean_up', 7, 9, 700), ('commons_harvest__open', 16, 8, 700), ('territory__rooms', 9, 9, 400),
-         ('territory__open', 9, 9, 400), ('coins', 2, 7, 700))
+         ('territory__open', 9, 9, 400), ('coins', 2, 7, 700), ('coop_mining', 6, 8, 500))
+only = sys.argv[1:]
 for name, players, n_act, B in CASES:
+  if only and name not in only:
+    continue
   roles = ('default',) * players
   blob = substrates.load_blob(name, roles)
   eng = engine.Engine(blob, B, seed=3)   # more envs than render teams, so that teams process several envs each
