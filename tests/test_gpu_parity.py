@@ -201,3 +201,18 @@ def test_coop_mining_rollout(coop_mining_blob, oracle):
   # ninth substrate; beams fired from component updates, two Ore components per ore object.
   stats = parity.compare_rollout(coop_mining_blob, oracle, num_envs=16, steps=1300, seed=41, actions_fn=_mine_heavy, pixels_every=5)
   assert stats['events'] > 200 and stats['rewards'] > 50
+
+
+def test_commons_harvest_config3_batch_size(commons16_blob, oracle):
+  # BASELINE.json config 3 size: 16 players x 8192 envs on one GPU; a sample of envs bit-for-bit against the oracle.
+  sample = [0, 1, 4095, 4096, 8191]
+  stats = parity.compare_rollout(commons16_blob, oracle, num_envs=8192, steps=40, seed=51, check_envs=sample, pixels_every=8)
+  assert stats['eaten'] > 5
+
+
+def test_territory_rooms_config4_shard_size(territory_blob, oracle):
+  # BASELINE.json config 4: 16384 envs sharded 2048 per GPU; this is rank 5's shard (env_index_base = 5 * 2048).
+  sample = [0, 1023, 2047]
+  stats = parity.compare_rollout(territory_blob, oracle, num_envs=2048, steps=40, seed=61, check_envs=sample,
+                                 pixels_every=8, env_index_base=5 * 2048)
+  assert stats['events'] > 0
