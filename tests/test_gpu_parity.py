@@ -216,3 +216,13 @@ def test_territory_rooms_config4_shard_size(territory_blob, oracle):
   stats = parity.compare_rollout(territory_blob, oracle, num_envs=2048, steps=40, seed=61, check_envs=sample,
                                  pixels_every=8, env_index_base=5 * 2048)
   assert stats['events'] > 0
+
+
+@pytest.mark.parametrize('name,players', [
+    ('clean_up', 7), ('commons_harvest__open', 7), ('commons_harvest__closed', 7), ('commons_harvest__partnership', 7),
+    ('territory__rooms', 9), ('territory__open', 9), ('territory__inside_out', 5), ('coins', 2), ('coop_mining', 6)])
+def test_config5_sweep_at_2048_envs(name, players, oracle):
+  # BASELINE.json config 5: the substrates of the sweep at 2048 envs each; sampled envs bit-for-bit against the oracle.
+  from meltingpot_b200 import substrates
+  blob = substrates.load_blob(name, ('default',) * players)
+  parity.compare_rollout(blob, oracle, num_envs=2048, steps=30, seed=71, check_envs=[0, 1000, 2047], pixels_every=6)
