@@ -70,8 +70,9 @@ typedef struct mp_buffers {
    * 4 claimed_resource(player), 5 destroyed_resource(player), 6 sanctioning(source, target),
    * 7 removal_due_to_sanctioning(source, target), 8 coin_consumed(player, 1 if the coin matched the player's type else 0;
    * coins/components.lua:133-137), 9 mining(player, ore type), 10 extraction(player, ore type),
-   * 11 extraction_pair(player_a, player_b | ore type << 8) (coop_mining/components.lua:203-234). Rows of one step are in no particular order; event_count may
-   * exceed max_events, in which case only the first max_events rows were kept. */
+   * 11 extraction_pair(player_a, player_b | ore type << 8) (coop_mining/components.lua:203-234). Rows of one step are in no particular order. max_events is the
+   * family's worst case for one step (per avatar: three events per beam-footprint cell + contact events), so
+   * event_count never exceeds it and no event is dropped. */
   int32_t* events;          /* i32 [B][max_events][3] */
   int32_t* event_count;     /* i32 [B] */
   int32_t max_events;
@@ -132,10 +133,12 @@ int mp_algorithmic_bytes(mp_handle h, uint64_t* per_env_step, uint64_t* render_p
  * (a dmlab2d env cannot be cloned); here the state is a handful of SoA arrays and the random numbers are
  * addressed by (seed, env, frame), so a byte copy is a complete checkpoint. A snapshot is an opaque string of
  * mp_state_size() bytes in host memory, valid for an engine created from the same blob with the same num_envs,
- * seed and env_index_base. mp_state_load re-renders the observations; both calls synchronise `stream`. */
+ * seed and env_index_base: the header records the env count, payload size, RNG key and a hash of the blob, and
+ * mp_state_load rejects (MP_E_INVALID) a buffer whose `nbytes` or header does not match this engine.
+ * mp_state_load re-renders the observations; both calls synchronise `stream`. */
 int mp_state_size(mp_handle h, uint64_t* bytes);
 int mp_state_save(mp_handle h, void* host_dst, void* stream);
-int mp_state_load(mp_handle h, const void* host_src, void* stream);
+int mp_state_load(mp_handle h, const void* host_src, uint64_t nbytes, void* stream);
 
 /* Diagnostic: how the renderer was laid out for this substrate: teams per CTA, threads per team, log2 of the pixel
  * rows per WORLD.RGB strip, shared memory bytes, atlas sprites, record stride (u16), staging bytes per warp, grid bytes. */

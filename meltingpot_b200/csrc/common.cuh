@@ -128,13 +128,14 @@ struct State {
   double* packed;      // [B][P+2] reward..., discount, step type: one buffer for the per-step all-gather
   uint8_t* rgb;
   uint8_t* world_rgb;
-  int32_t* events;     // [B][MP_MAX_EVENTS][3] (type, a, b) of the current step, unordered (see emit_event)
-  int32_t* n_events;   // [B] events emitted this step (may exceed MP_MAX_EVENTS: the excess is dropped)
+  int32_t* events;     // [B][max_events][3] (type, a, b) of the current step, unordered (see emit_event)
+  int32_t* n_events;   // [B] events emitted this step
+  int max_events;      // rows per env: the family's worst case for one step (mp_create), so nothing is ever dropped
 };
 
 // Events of the current step (the reference's events:add calls on the hot path). Types follow
 // the order of oracle/mp_oracle.c; player indices are 1-based as in Lua.
-#define MP_MAX_EVENTS 64
+#define MP_MIN_EVENTS 64  // floor of State::max_events
 enum { EV_ZAP = 1, EV_EDIBLE_CONSUMED = 2, EV_PLAYER_CLEANED = 3, EV_CLAIMED_RESOURCE = 4, EV_DESTROYED_RESOURCE = 5,
        EV_SANCTIONING = 6, EV_REMOVAL = 7, EV_COIN_CONSUMED = 8 /* a = player, b = 1 match / 0 mismatch */,
        EV_MINING = 9 /* a = player, b = ore type */, EV_EXTRACTION = 10 /* a = player, b = ore type */,
@@ -144,8 +145,8 @@ enum { EV_ZAP = 1, EV_EDIBLE_CONSUMED = 2, EV_PLAYER_CLEANED = 3, EV_CLAIMED_RES
 // step is unspecified (hosts sort); the per-env counter is zeroed at kernel entry.
 __device__ __forceinline__ void emit_event(const State& S, int b, int type, int a0, int a1) {
   const int i = atomicAdd(&S.n_events[b], 1);
-  if (i < MP_MAX_EVENTS) {
-    int32_t* e = S.events + ((size_t)b * MP_MAX_EVENTS + i) * 3;
+  if (i < S.max_events) {  // (always true: max_events bounds what one step can emit; kept as a memory-safety guard)
+    int32_t* e = S.events + ((size_t)b * S.max_events + i) * 3;
     e[0] = type; e[1] = a0; e[2] = a1;
   }
 }

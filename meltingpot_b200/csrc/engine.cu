@@ -60,7 +60,8 @@ bool get_section(const void* blob, size_t n, const char* name, int dtype, Sectio
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 constexpr int kRenderSmemLimit = 227 * 1024 - 2560;  // dynamic shared memory: the 227 KB opt-in maximum less k_render's static arrays
-constexpr int kMaxAtlasSprites = 96;  // sprites incl. pre-merged ones kept in shared memory by k_render
+constexpr int kMaxAtlasSprites = 96;
+#define MP_MAX_DEVICES 64  // sprites incl. pre-merged ones kept in shared memory by k_render
 
 // Beam footprint in visiting order (policy A.8): centre ray, then for each side the lateral cells
 // outwards, each followed by its forward ray of length `length - k`.
@@ -109,6 +110,7 @@ struct mp_engine {
   int black_sprite = -1;
   std::vector<std::pair<void*, size_t>> state_spans;  // what mp_state_save / mp_state_load copy
   uint64_t state_bytes = 0;
+  uint64_t blob_hash = 0;  // FNV-1a of the compiled blob: a snapshot only loads into an engine built from the same blob
 
   template <typename T>
   int upload(const std::vector<T>& host, const T** out) {
@@ -634,13 +636,19 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   int n_dev = 0;
   cudaError_t e = cudaGetDeviceCount(&n_dev);
   if (e != cudaSuccess || n_dev == 0) return fail(MP_E_NO_DEVICE, "no CUDA device available (%s); this engine has no CPU path", cudaGetErrorString(e));
-  if (device < 0 || device >= n_dev) return fail(MP_E_INVALID, "device %d out of range (0..%d)", device, n_dev - 1);
+  if (device < 0 || device >= n_dev || device >= MP_MAX_DEVICES) return fail(MP_E_INVALID, "device %d out of range (0..%d)", device, n_dev - 1);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(MP_E_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
   DeviceGuard guard(device);
   mp_engine* E = new mp_engine();
   E->device = device; E->B = num_envs; E->flags = flags; E->sm_count = prop.multiProcessorCount;
+  {
+    uint64_t hsh = 1469598103934665603ull;
+    const uint8_t* bp = static_cast<const uint8_t*>(blob);
+    for (size_t i = 0; i < blob_bytes; ++i) { hsh ^= bp[i]; hsh *= 1099511628211ull; }
+    E->blob_hash = hsh;
+  }
   int rc = build_tables(E, blob, blob_bytes);
   if (rc == MP_OK) rc = build_plan(E);
   if (rc != MP_OK) { mp_destroy(E); return rc; }
@@ -648,13 +656,19 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   State& S = E->S;
   S.B = num_envs; S.seed = seed + env_index_base;
   const size_t B = num_envs, P = T.P;
+  {  // Worst case of events one step can emit per env: per avatar, every cell of every beam footprint can carry a hit
+     // with up to three events (zap + sanctioning + removal), plus the contact / regrowth events (<= 4) and the pair
+     // events of coop_mining (<= P). Sized so that emit_event never drops a row.
+    const int beam_cells = T.zap_geom.n + T.clean_geom.n + T.claim_geom.n + T.brush_geom.n;
+    S.max_events = round_up(std::max(MP_MIN_EVENTS, T.P * (3 * beam_cells + 4 + T.P)), 16);
+  }
   S.fam_u8_stride = std::max(16, RU_COUNT * T.nR_pad); S.fam_u16_stride = std::max(16, RS_COUNT * T.nR_pad);
   if ((rc = E->alloc(B * T.L * T.cells_pad, &S.grid)) || (rc = E->alloc(B * P * 4, &S.avatar)) || (rc = E->alloc(B * P * 4, &S.av_timer)) ||
       (rc = E->alloc(B * T.nA_pad, &S.apple)) || (rc = E->alloc(B * T.nD_pad, &S.dirt)) || (rc = E->alloc(B * T.nW_pad, &S.water)) || (rc = E->alloc(B * T.nA_pad, &S.apple_count)) || (rc = E->alloc(B * (size_t)S.fam_u8_stride, &S.fam_u8)) || (rc = E->alloc(B * (size_t)S.fam_u16_stride, &S.fam_u16)) || (rc = E->alloc(B * P * 8, &S.av_extra)) || (rc = E->alloc(B * (P + 2), &S.packed)) ||
       (rc = E->alloc(B * ENV_COLS, &S.env)) || (rc = E->alloc(B * P, &S.reward)) || (rc = E->alloc(B, &S.discount)) ||
       (rc = E->alloc(B, &S.step_type)) || (rc = E->alloc(std::max<size_t>(1, T.n_scalar) * B * P, &S.scalar_obs)) ||
       (rc = E->alloc(B * P * E->R.player_bytes, &S.rgb)) || (rc = E->alloc(B * (size_t)E->R.world_bytes, &S.world_rgb)) ||
-      (rc = E->alloc(B * MP_MAX_EVENTS * 3, &S.events)) || (rc = E->alloc(B, &S.n_events)) ||
+      (rc = E->alloc(B * (size_t)S.max_events * 3, &S.events)) || (rc = E->alloc(B, &S.n_events)) ||
       (rc = E->alloc(B * P, &E->d_actions))) {
     mp_destroy(E);
     return rc;
@@ -670,7 +684,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
     span(S.packed, B * (P + 2) * sizeof(*S.packed)); span(S.env, B * ENV_COLS * sizeof(*S.env));
     span(S.reward, B * P * sizeof(*S.reward)); span(S.discount, B * sizeof(*S.discount));
     span(S.step_type, B * sizeof(*S.step_type)); span(S.scalar_obs, ns * B * P * sizeof(*S.scalar_obs));
-    span(S.events, B * MP_MAX_EVENTS * 3 * sizeof(*S.events)); span(S.n_events, B * sizeof(*S.n_events));
+    span(S.events, B * (size_t)S.max_events * 3 * sizeof(*S.events)); span(S.n_events, B * sizeof(*S.n_events));
   }
   // episode counter starts at -1 so that the first reset plays episode 0; envs start "done".
   {
@@ -688,12 +702,21 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
     else if (ncp <= 4 && ncw <= 5) E->render_fn = k_render<4, 5>;
     else { mp_destroy(E); return fail(MP_E_UNSUPPORTED, "view of %d cells / map of %d cells wide (max 16 / 40)", E->R.view_w, T.W); }
   }
-  cudaError_t ce = cudaFuncSetAttribute(E->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, E->R.smem_bytes);
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_clean_up, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_commons, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_territory, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_coins, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_mining, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(E->step_smem * 4));
+  // The attribute belongs to the kernel function, not to this handle: engines that share an instantiation must not
+  // lower each other's limit, so the renderer always gets the opt-in maximum and the step kernels only ever raise theirs.
+  cudaError_t ce = cudaFuncSetAttribute(E->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmemLimit);
+  {
+    static int step_smem_max[MP_MAX_DEVICES] = {};
+    const int need = (int)(E->step_smem * 4);
+    if (ce == cudaSuccess && need > 48 * 1024 && need > step_smem_max[device]) {
+      ce = cudaFuncSetAttribute(k_step_clean_up, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_commons, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_territory, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_coins, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_mining, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+      if (ce == cudaSuccess) step_smem_max[device] = need;
+    }
+  }
   if (ce != cudaSuccess) { mp_destroy(E); return fail(MP_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)); }
   mp_buffers& bf = E->buffers;
   bf.num_envs = num_envs; bf.num_players = T.P; bf.rgb_h = E->R.view_h * 8; bf.rgb_w = E->R.view_w * 8;
@@ -701,7 +724,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   bf.rgb = S.rgb; bf.world_rgb = S.world_rgb; bf.reward = S.reward; bf.discount = S.discount; bf.step_type = S.step_type;
   bf.scalar_obs = S.scalar_obs; bf.avatar_state = S.avatar; bf.grid = S.grid; bf.timestep_packed = S.packed;
   bf.grid_layers = T.L; bf.grid_cells = T.cells; bf.grid_cells_padded = T.cells_pad;
-  bf.events = S.events; bf.event_count = S.n_events; bf.max_events = MP_MAX_EVENTS;
+  bf.events = S.events; bf.event_count = S.n_events; bf.max_events = S.max_events;
   // observations + scalars + actions + one read and one write of the compact grid.
   E->render_bytes = (uint64_t)P * E->R.player_bytes + (uint64_t)E->R.world_bytes + (uint64_t)T.L * T.cells * 2;
   E->algo_bytes = (uint64_t)P * E->R.player_bytes + (uint64_t)E->R.world_bytes + 8ull * ((1 + T.n_scalar) * P + 2) + 8ull * P + 2ull * T.L * T.cells * 2;
@@ -782,7 +805,7 @@ int mp_reset_host(mp_handle h, const mp_host_outputs* out, void* stream) {
 }
 
 namespace {
-struct SnapshotHeader { char magic[4]; uint32_t version; uint64_t num_envs, payload_bytes, n_spans; };
+struct SnapshotHeader { char magic[4]; uint32_t version; uint64_t num_envs, payload_bytes, n_spans, rng_key0, blob_hash; };
 }
 
 int mp_state_size(mp_handle h, uint64_t* bytes) {
@@ -795,7 +818,7 @@ int mp_state_save(mp_handle h, void* host_dst, void* stream) {
   if (!h || !host_dst) return fail(MP_E_INVALID, "mp_state_save: null argument");
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
-  SnapshotHeader hd{{'M', 'P', 'S', '1'}, 1u, (uint64_t)h->B, h->state_bytes, (uint64_t)h->state_spans.size()};
+  SnapshotHeader hd{{'M', 'P', 'S', '2'}, 2u, (uint64_t)h->B, h->state_bytes, (uint64_t)h->state_spans.size(), h->S.seed, h->blob_hash};
   memcpy(host_dst, &hd, sizeof(hd));
   uint8_t* dst = static_cast<uint8_t*>(host_dst) + sizeof(hd);
   for (const auto& sp : h->state_spans) {
@@ -806,14 +829,21 @@ int mp_state_save(mp_handle h, void* host_dst, void* stream) {
   return MP_OK;
 }
 
-int mp_state_load(mp_handle h, const void* host_src, void* stream) {
+int mp_state_load(mp_handle h, const void* host_src, uint64_t nbytes, void* stream) {
   if (!h || !host_src) return fail(MP_E_INVALID, "mp_state_load: null argument");
+  if (nbytes < sizeof(SnapshotHeader)) return fail(MP_E_INVALID, "mp_state_load: %llu bytes is shorter than a snapshot header", (unsigned long long)nbytes);
   SnapshotHeader hd;
   memcpy(&hd, host_src, sizeof(hd));
-  if (memcmp(hd.magic, "MPS1", 4) != 0 || hd.version != 1u) return fail(MP_E_INVALID, "mp_state_load: not a snapshot");
+  if (memcmp(hd.magic, "MPS2", 4) != 0 || hd.version != 2u) return fail(MP_E_INVALID, "mp_state_load: not a snapshot (or one of an older engine)");
   if (hd.num_envs != (uint64_t)h->B || hd.payload_bytes != h->state_bytes || hd.n_spans != h->state_spans.size())
     return fail(MP_E_INVALID, "mp_state_load: snapshot of %llu envs / %llu bytes does not fit this engine (%d envs / %llu bytes)",
                 (unsigned long long)hd.num_envs, (unsigned long long)hd.payload_bytes, h->B, (unsigned long long)h->state_bytes);
+  if (nbytes != sizeof(SnapshotHeader) + hd.payload_bytes)
+    return fail(MP_E_INVALID, "mp_state_load: buffer of %llu bytes, snapshot needs %llu (truncated?)", (unsigned long long)nbytes,
+                (unsigned long long)(sizeof(SnapshotHeader) + hd.payload_bytes));
+  if (hd.blob_hash != h->blob_hash) return fail(MP_E_INVALID, "mp_state_load: snapshot was taken from a different compiled substrate");
+  if (hd.rng_key0 != h->S.seed) return fail(MP_E_INVALID, "mp_state_load: snapshot was taken with a different seed / env_index_base (key %llu, engine %llu)",
+                                            (unsigned long long)hd.rng_key0, (unsigned long long)h->S.seed);
   DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const uint8_t* src = static_cast<const uint8_t*>(host_src) + sizeof(hd);

@@ -84,7 +84,7 @@ def load_library() -> ctypes.CDLL:
                                        ctypes.POINTER(ctypes.c_uint64)]
   lib.mp_state_size.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
   lib.mp_state_save.argtypes = [vp, vp, vp]
-  lib.mp_state_load.argtypes = [vp, vp, vp]
+  lib.mp_state_load.argtypes = [vp, vp, ctypes.c_uint64, vp]
   lib.mp_debug_render_plan.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
   lib.mp_debug_render_tables.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), vp, vp]
   lib.mp_last_error.restype = ctypes.c_char_p
@@ -114,11 +114,29 @@ def _check(rc: int) -> None:
     raise EngineError(f'mp_engine error {rc}: {msg}')
 
 
+class _Handle:
+  """Owns one mp_handle. Every tensor view of the engine's buffers holds a reference, so the device memory is
+  released (mp_destroy) only once the Engine has been closed AND the last view is gone: a retained observation
+  tensor can never dangle."""
+
+  def __init__(self, lib, handle):
+    self._lib = lib
+    self.h = handle
+
+  def __del__(self):
+    try:
+      if self.h:
+        self._lib.mp_destroy(self.h)
+        self.h = None
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+
 class _CudaView:
   """Exposes a raw device pointer through __cuda_array_interface__ (v2)."""
 
   def __init__(self, ptr: int, shape, typestr: str, owner):
-    self._owner = owner  # keeps the engine alive while tensors exist
+    self._owner = owner  # the _Handle: keeps the device memory alive while tensors exist
     self.__cuda_array_interface__ = {
         'shape': tuple(int(s) for s in shape), 'typestr': typestr,
         'data': (int(ptr), False), 'version': 2, 'strides': None,
@@ -146,6 +164,7 @@ class Engine:
                                self.device, ctypes.c_uint64(seed),
                                ctypes.c_uint64(env_index_base),
                                ctypes.c_uint32(flags), ctypes.byref(handle)))
+    self._owner = _Handle(self._lib, handle)
     self._h = handle
     bufs = MpBuffers()
     _check(self._lib.mp_get_buffers(self._h, ctypes.byref(bufs)))
@@ -157,7 +176,7 @@ class Engine:
     dev = torch.device('cuda', self.device)
 
     def view(ptr, shape, typestr, dtype):
-      return torch.as_tensor(_CudaView(ptr, shape, typestr, self), device=dev, dtype=dtype)
+      return torch.as_tensor(_CudaView(ptr, shape, typestr, self._owner), device=dev, dtype=dtype)
 
     self.rgb = view(bufs.rgb, (B, P, bufs.rgb_h, bufs.rgb_w, 3), '|u1', torch.uint8)
     self.world_rgb = view(bufs.world_rgb, (B, bufs.world_h, bufs.world_w, 3), '|u1', torch.uint8)
@@ -172,10 +191,17 @@ class Engine:
     self.event_count = view(bufs.event_count, (B,), '<i4', torch.int32)
 
   # -- lifecycle -----------------------------------------------------------------
+  _VIEWS = ('rgb', 'world_rgb', 'reward', 'discount', 'step_type', 'scalar_obs', 'avatar_state', 'grid',
+            'timestep_packed', 'events', 'event_count')
+
   def close(self) -> None:
+    """Drops this object's references. mp_destroy runs when the last tensor view handed out has been released too
+    (tensors a caller still holds stay readable; the engine itself can no longer be stepped)."""
     if getattr(self, '_h', None):
-      self._lib.mp_destroy(self._h)
       self._h = None
+      for name in self._VIEWS:
+        self.__dict__.pop(name, None)
+      self._owner = None
 
   def __del__(self):
     try:
@@ -271,8 +297,9 @@ class Engine:
     return buf.raw
 
   def load_state(self, snapshot: bytes, stream=None) -> None:
+    snapshot = bytes(snapshot)
     buf = ctypes.create_string_buffer(snapshot, len(snapshot))
-    _check(self._lib.mp_state_load(self._h, buf, self._stream(stream)))
+    _check(self._lib.mp_state_load(self._h, buf, ctypes.c_uint64(len(snapshot)), self._stream(stream)))
 
   def render_plan(self):
     """Layout the renderer chose for this substrate (diagnostic)."""

@@ -65,6 +65,8 @@ def lib() -> ctypes.CDLL:
     L.oracle_batch_destroy.argtypes = [vp]
     L.oracle_batch_step_random.restype = ctypes.c_long
     L.oracle_batch_step_random.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.oracle_batch_step_actions.argtypes = [vp, i32p, ctypes.c_int]
+    L.oracle_batch_dump.argtypes = [vp, ctypes.c_int] + [vp] * 8 + [ctypes.c_int, vp, vp]
     L.oracle_batch_checksum.restype = ctypes.c_uint64
     L.oracle_batch_checksum.argtypes = [vp]
     _lib = L
@@ -211,6 +213,30 @@ class OracleBatch:
 
   def checksum(self) -> int:
     return int(lib().oracle_batch_checksum(self._h))
+
+  def step_actions(self, actions, n_threads: int) -> None:
+    """Steps every env with the given discrete actions (int32 [n_envs, P]) on host threads."""
+    a = np.ascontiguousarray(actions, np.int32)
+    assert a.ndim == 2 and a.shape[0] == self.n_envs
+    lib().oracle_batch_step_actions(self._h, _ptr(a, ctypes.c_int32), n_threads)
+
+  def dump(self, n_threads: int, shapes, pixels: bool = False, max_events: int = 256):
+    """Every output of every env, laid out like the engine's buffers. `shapes` = dict(P, L, cells, n_scalar,
+    rgb=(h, w), world=(h, w)). Event rows are sorted per env."""
+    B, P = self.n_envs, shapes['P']
+    out = {
+        'reward': np.zeros((B, P), np.float64), 'discount': np.zeros((B,), np.float64),
+        'step_type': np.zeros((B,), np.int64), 'scalar_obs': np.zeros((max(shapes['n_scalar'], 1), B, P), np.float64),
+        'avatars': np.zeros((B, P, 4), np.int32), 'grid': np.zeros((B, shapes['L'], shapes['cells']), np.uint16),
+        'events': np.zeros((B, max_events, 3), np.int32), 'n_events': np.zeros((B,), np.int32),
+    }
+    if pixels:
+      out['rgb'] = np.zeros((B, P) + tuple(shapes['rgb']) + (3,), np.uint8)
+      out['world'] = np.zeros((B,) + tuple(shapes['world']) + (3,), np.uint8)
+    vp = lambda k: out[k].ctypes.data if k in out else None
+    lib().oracle_batch_dump(self._h, n_threads, vp('reward'), vp('discount'), vp('step_type'), vp('scalar_obs'),
+                            vp('avatars'), vp('grid'), vp('events'), vp('n_events'), max_events, vp('rgb'), vp('world'))
+    return out
 
   def close(self):
     if self._h:

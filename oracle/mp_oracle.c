@@ -1243,3 +1243,82 @@ long oracle_batch_step_random(OrBatch* bt, int n_steps, int n_threads, int rende
   return total;
 }
 uint64_t oracle_batch_checksum(const OrBatch* bt) { return bt->sum; }
+
+/* Whole-batch checking (tests only): step every env with caller-given actions on host threads, then dump every
+ * output of every env into caller-owned arrays laid out like the engine's device buffers (include/mp_engine.h), so
+ * a parity test compares whole batches with one array comparison per field instead of sampling envs. */
+typedef struct { OrBatch* bt; int b0, b1; const int32_t* actions; } StepArgs;
+static void* step_actions_worker(void* argp) {
+  StepArgs* a = (StepArgs*)argp;
+  for (int b = a->b0; b < a->b1; ++b) { OrEnv* e = a->bt->envs[b]; oracle_step(e, a->actions + (size_t)b * e->P); }
+  return 0;
+}
+void oracle_batch_step_actions(OrBatch* bt, const int32_t* actions, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > bt->n_envs) n_threads = bt->n_envs;
+  pthread_t* th = (pthread_t*)calloc(n_threads, sizeof(pthread_t));
+  StepArgs* args = (StepArgs*)calloc(n_threads, sizeof(StepArgs));
+  for (int t = 0; t < n_threads; ++t) {
+    StepArgs a = {bt, (int)((long)bt->n_envs * t / n_threads), (int)((long)bt->n_envs * (t + 1) / n_threads), actions};
+    args[t] = a;
+    pthread_create(&th[t], 0, step_actions_worker, &args[t]);
+  }
+  for (int t = 0; t < n_threads; ++t) pthread_join(th[t], 0);
+  free(th); free(args);
+}
+typedef struct {
+  OrBatch* bt; int b0, b1, max_ev;
+  double* reward; double* discount; int64_t* step_type; double* scalar_obs; int32_t* avatars; uint16_t* grid;
+  int32_t* events; int32_t* n_events; uint8_t* rgb; uint8_t* world;
+} DumpArgs;
+static int cmp_event(const void* pa, const void* pb) {
+  const int32_t* a = (const int32_t*)pa; const int32_t* b = (const int32_t*)pb;
+  for (int i = 0; i < 3; ++i) if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  return 0;
+}
+static void* dump_worker(void* argp) {
+  DumpArgs* a = (DumpArgs*)argp;
+  const int B = a->bt->n_envs;
+  double tmp[OR_MAX_PLAYERS * 8];
+  for (int b = a->b0; b < a->b1; ++b) {
+    OrEnv* e = a->bt->envs[b];
+    const int P = e->P, cells = e->W * e->H;
+    if (a->reward) oracle_get_rewards(e, a->reward + (size_t)b * P);
+    if (a->discount) a->discount[b] = oracle_get_discount(e);
+    if (a->step_type) a->step_type[b] = oracle_get_step_type(e);
+    if (a->scalar_obs && e->n_scalar) {
+      oracle_get_scalar_obs(e, tmp);
+      for (int k = 0; k < e->n_scalar; ++k) for (int p = 0; p < P; ++p) a->scalar_obs[((size_t)k * B + b) * P + p] = tmp[p * e->n_scalar + k];
+    }
+    if (a->avatars) oracle_get_avatars(e, a->avatars + (size_t)b * P * 4);
+    if (a->grid) oracle_get_grid(e, a->grid + (size_t)b * e->L * cells);
+    if (a->events) {
+      int32_t* ev = a->events + (size_t)b * a->max_ev * 3;
+      int n = oracle_get_events(e, ev, a->max_ev);
+      a->n_events[b] = n;
+      qsort(ev, n < a->max_ev ? n : a->max_ev, 3 * sizeof(int32_t), cmp_event);
+    }
+    if (a->rgb) {
+      const size_t pb = (size_t)(e->view_l + e->view_r + 1) * (e->view_f + e->view_b + 1) * e->S * e->S * 3;
+      for (int p = 0; p < P; ++p) oracle_render_player(e, p, a->rgb + ((size_t)b * P + p) * pb);
+    }
+    if (a->world) oracle_render_world(e, a->world + (size_t)b * cells * e->S * e->S * 3);
+  }
+  return 0;
+}
+/* Any output pointer may be NULL. events rows are sorted per env; n_events holds the true count. */
+void oracle_batch_dump(OrBatch* bt, int n_threads, double* reward, double* discount, int64_t* step_type, double* scalar_obs,
+                       int32_t* avatars, uint16_t* grid, int32_t* events, int32_t* n_events, int max_ev, uint8_t* rgb, uint8_t* world) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > bt->n_envs) n_threads = bt->n_envs;
+  pthread_t* th = (pthread_t*)calloc(n_threads, sizeof(pthread_t));
+  DumpArgs* args = (DumpArgs*)calloc(n_threads, sizeof(DumpArgs));
+  for (int t = 0; t < n_threads; ++t) {
+    DumpArgs a = {bt, (int)((long)bt->n_envs * t / n_threads), (int)((long)bt->n_envs * (t + 1) / n_threads), max_ev,
+                  reward, discount, step_type, scalar_obs, avatars, grid, events, n_events, rgb, world};
+    args[t] = a;
+    pthread_create(&th[t], 0, dump_worker, &args[t]);
+  }
+  for (int t = 0; t < n_threads; ++t) pthread_join(th[t], 0);
+  free(th); free(args);
+}

@@ -37,13 +37,13 @@ def test_clean_up_clean_river_apples_grow_and_get_eaten(clean_river_blob, oracle
 
 
 def test_clean_up_full_batch_size_invariants(clean_up_blob, oracle):
-  # BASELINE.json config 2 size: 4096 envs. A sample of envs is compared bit-for-bit with the oracle;
-  # the whole batch is checked through size-independent properties.
+  # BASELINE.json config 2 size: 4096 envs. EVERY env is compared with the oracle (state, rewards, events on every
+  # step; every RGB byte every 10 steps); the batch is also checked through size-independent properties.
   import torch
   from meltingpot_b200 import engine
   B = 4096
-  sample = [0, 1, 777, 2048, 4095]
-  parity.compare_rollout(clean_up_blob, oracle, num_envs=B, steps=60, seed=21, check_envs=sample, pixels_every=10)
+  stats = parity.compare_batch(clean_up_blob, oracle, num_envs=B, steps=60, seed=21, pixels_every=10)
+  assert stats['pixel_checks'] == 7 and stats['events'] > 1000
   eng = engine.Engine(clean_up_blob, B, seed=21)
   eng.reset()
   first = eng.world_rgb.clone()
@@ -204,25 +204,24 @@ def test_coop_mining_rollout(coop_mining_blob, oracle):
 
 
 def test_commons_harvest_config3_batch_size(commons16_blob, oracle):
-  # BASELINE.json config 3 size: 16 players x 8192 envs on one GPU; a sample of envs bit-for-bit against the oracle.
-  sample = [0, 1, 4095, 4096, 8191]
-  stats = parity.compare_rollout(commons16_blob, oracle, num_envs=8192, steps=40, seed=51, check_envs=sample, pixels_every=8)
-  assert stats['eaten'] > 5
+  # BASELINE.json config 3 size: 16 players x 8192 envs on one GPU; every env against the oracle.
+  stats = parity.compare_batch(commons16_blob, oracle, num_envs=8192, steps=40, seed=51, pixels_every=20)
+  assert stats['events'] > 1000 and stats['pixel_checks'] == 3
 
 
 def test_territory_rooms_config4_shard_size(territory_blob, oracle):
   # BASELINE.json config 4: 16384 envs sharded 2048 per GPU; this is rank 5's shard (env_index_base = 5 * 2048).
-  sample = [0, 1023, 2047]
-  stats = parity.compare_rollout(territory_blob, oracle, num_envs=2048, steps=40, seed=61, check_envs=sample,
-                                 pixels_every=8, env_index_base=5 * 2048)
-  assert stats['events'] > 0
+  # Every env of the shard against the oracle.
+  stats = parity.compare_batch(territory_blob, oracle, num_envs=2048, steps=40, seed=61, pixels_every=8, env_index_base=5 * 2048)
+  assert stats['events'] > 0 and stats['pixel_checks'] == 6
 
 
 @pytest.mark.parametrize('name,players', [
     ('clean_up', 7), ('commons_harvest__open', 7), ('commons_harvest__closed', 7), ('commons_harvest__partnership', 7),
     ('territory__rooms', 9), ('territory__open', 9), ('territory__inside_out', 5), ('coins', 2), ('coop_mining', 6)])
 def test_config5_sweep_at_2048_envs(name, players, oracle):
-  # BASELINE.json config 5: the substrates of the sweep at 2048 envs each; sampled envs bit-for-bit against the oracle.
+  # BASELINE.json config 5: the substrates of the sweep at 2048 envs each; every env against the oracle.
   from meltingpot_b200 import substrates
   blob = substrates.load_blob(name, ('default',) * players)
-  parity.compare_rollout(blob, oracle, num_envs=2048, steps=30, seed=71, check_envs=[0, 1000, 2047], pixels_every=6)
+  stats = parity.compare_batch(blob, oracle, num_envs=2048, steps=30, seed=71, pixels_every=6)
+  assert stats['pixel_checks'] == 6
