@@ -76,6 +76,15 @@ typedef struct mp_buffers {
   int32_t* events;          /* i32 [B][max_events][3] */
   int32_t* event_count;     /* i32 [B] */
   int32_t max_events;
+  /* reward | discount | step_type | scalar_obs above are carved, in this order, from ONE device allocation of
+   * scalar_block_bytes bytes starting at scalar_block (every element is 8 bytes), so a host consumer can fetch all
+   * scalar outputs of a step with a single copy (mp_host_outputs.scalar_block). */
+  void* scalar_block;
+  uint64_t scalar_block_bytes;
+  /* After mp_exchange_create: f64 [2][gathered_world * B][P + 2], the timestep_packed rows of EVERY rank's envs in
+   * global env order (rank r's envs at rows [r * B, (r + 1) * B)); slot (step & 1) holds the most recent step. */
+  double* gathered;
+  int32_t gathered_world;
 } mp_buffers;
 
 /* Replaces dmlab2d.Lab2d(...) + dmlab2d.Environment(...) (builder.py:182-187) for `num_envs`
@@ -119,9 +128,46 @@ typedef struct mp_host_outputs {
   double* discount;
   int64_t* step_type;
   double* scalar_obs;
+  void* scalar_block; /* if non-NULL: receives mp_buffers.scalar_block (scalar_block_bytes bytes) in one transfer and the
+                         four scalar pointers above are ignored */
 } mp_host_outputs;
 int mp_step_host(mp_handle h, const int32_t* actions_host, const mp_host_outputs* out, void* stream);
 int mp_reset_host(mp_handle h, const mp_host_outputs* out, void* stream);
+
+/* Pipelined form of mp_step_host for host consumers that alternate two output buffer sets (the usual double-buffered
+ * actor loop): enqueues H2D(actions) -> state transition -> rendering on `stream` and the device->host copies of
+ * the step's outputs on an internal copy stream, then returns WITHOUT synchronising. `slot` (0 or 1) names the
+ * device-side image / scalar staging set used; consecutive calls alternate slots, so step t+1's kernels run while
+ * step t's observations are still crossing PCIe. mp_wait(h, slot) blocks until the outputs of the last call on
+ * that slot are complete in the host buffers. `actions_host` and `out`'s buffers must stay untouched from the call
+ * until mp_wait on the same slot returns. Steps are still applied in call order (one state per env). */
+int mp_step_host_async(mp_handle h, const int32_t* actions_host, const mp_host_outputs* out, int slot, void* stream);
+int mp_wait(mp_handle h, int slot);
+
+/* Stacked timestep across GPUs (the path's only exchange). Envs shard over ranks with no
+ * data-path collective; what every rank needs back is ONE stacked [world * B] tensor of reward / discount / step type.
+ * Instead of a collective kernel per step, every rank's state-transition kernel writes its rows straight into every
+ * rank's `gathered` buffer through NVLink peer mappings (P + 2 remote stores per env and rank) and the last warp of
+ * the launch raises a per-rank flag; consumers enqueue mp_exchange_wait (a one-warp kernel that fits beside the
+ * persistent renderer) before reading mp_buffers.gathered.
+ *   mp_exchange_create   allocates this rank's exchange block: 256 bytes of per-rank flags followed by `gathered`
+ *                        (one allocation, so one IPC handle shares it); returns its device pointer and size;
+ *   mp_ipc_export/open   turn a device pointer into a 64-byte CUDA IPC handle + offset inside the driver allocation
+ *                        and back (one process per GPU: exchange handle and offset through torch.distributed);
+ *   mp_enable_peer_access for ranks that live in ONE process (tests): plain cudaDeviceEnablePeerAccess;
+ *   mp_exchange_connect  takes, in rank order, every rank's block as mapped into this process (its own entry = the
+ *                        pointer mp_exchange_create returned); from then on every mp_step / mp_step_state /
+ *                        mp_reset publishes. All ranks must issue the same sequence of steps and resets (the slot
+ *                        is the parity of the launch sequence number);
+ *   mp_exchange_wait     enqueues on `stream` the wait for every rank's flag of the most recent step;
+ *   mp_exchange_slot     which half of `gathered` the most recent step was written to (and its sequence number). */
+int mp_exchange_create(mp_handle h, int rank, int world, void** block, uint64_t* block_bytes);
+int mp_ipc_export(const void* device_ptr, void* handle64, uint64_t* offset);
+int mp_ipc_open(int device, const void* handle64, uint64_t offset, void** device_ptr);
+int mp_enable_peer_access(int device, int peer_device);
+int mp_exchange_connect(mp_handle h, void* const* peer_blocks);
+int mp_exchange_wait(mp_handle h, void* stream);
+int mp_exchange_slot(mp_handle h, int* slot, uint64_t* step);
 
 /* Number of kernels this engine has launched since creation (all streams). */
 int mp_launch_count(mp_handle h, uint64_t* out);

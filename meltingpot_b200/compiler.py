@@ -74,42 +74,63 @@ _HIT_OF = {'Zapper': ('zapHit', 'beamZap', 'BeamZap'),
 # ---------------------------------------------------------------------------
 # Loading reference configs without executing meltingpot/__init__.py
 # ---------------------------------------------------------------------------
-def _stub_package(name: str, path: str) -> None:
-  if name not in sys.modules:
-    module = types.ModuleType(name)
-    module.__path__ = [path]
-    sys.modules[name] = module
-
-
 def reference_root() -> Optional[str]:
-  for cand in (os.environ.get('MELTINGPOT_REFERENCE_ROOT'), '/root/reference'):
-    if cand and os.path.isdir(os.path.join(cand, 'meltingpot', 'configs')):
-      return cand
+  """The Melting Pot checkout to compile from: ONLY the one named by MELTINGPOT_REFERENCE_ROOT.
+
+  Compiling imports and executes the checkout's config modules, so no location is ever guessed: without the
+  variable (or an explicit `root` argument) there is no reference, and `substrates.load_blob` serves committed
+  blobs only.
+  """
+  cand = os.environ.get('MELTINGPOT_REFERENCE_ROOT')
+  if cand and os.path.isdir(os.path.join(cand, 'meltingpot', 'configs')):
+    return cand
   return None
 
 
-def load_reference_config(name: str, root: Optional[str] = None):
-  """Imports `meltingpot.configs.substrates.<name>` from a reference checkout.
+import contextlib  # pylint: disable=g-import-not-at-top,g-bad-import-order
 
-  The package `__init__` pulls in dmlab2d/chex/reactivex which are absent here,
-  so namespace stubs are registered for the parent packages instead
-  (`/root/reference/meltingpot/__init__.py:18`).
+
+@contextlib.contextmanager
+def reference_packages(root: Optional[str] = None):
+  """Temporarily makes `meltingpot.*` import from a reference checkout, without running its package __init__.
+
+  The reference's `meltingpot/__init__.py` pulls in dmlab2d / chex / reactivex (absent here;
+  `/root/reference/meltingpot/__init__.py:18`), so namespace stubs stand in for the parent packages. Whatever
+  `meltingpot*` modules were loaded before (this repo's own `meltingpot` alias package, or a real dm-meltingpot
+  install) are put back on exit and every module imported from the checkout is dropped again, so the process is
+  not left with shadowing stubs.
   """
   from meltingpot_b200 import shims  # pylint: disable=g-import-not-at-top
   shims.install()
   root = root or reference_root()
   if root is None:
-    raise FileNotFoundError('no Melting Pot reference checkout found; set '
-                            'MELTINGPOT_REFERENCE_ROOT')
+    raise FileNotFoundError('no Melting Pot reference checkout: set MELTINGPOT_REFERENCE_ROOT (nothing is guessed)')
   base = os.path.join(root, 'meltingpot')
-  _stub_package('meltingpot', base)
-  _stub_package('meltingpot.utils', os.path.join(base, 'utils'))
-  _stub_package('meltingpot.utils.substrates',
-                os.path.join(base, 'utils', 'substrates'))
-  _stub_package('meltingpot.configs', os.path.join(base, 'configs'))
+  mine = lambda k: k == 'meltingpot' or k.startswith('meltingpot.')
+  saved = {k: v for k, v in sys.modules.items() if mine(k)}
+  for k in saved:
+    del sys.modules[k]
+  try:
+    for name, path in (('meltingpot', base), ('meltingpot.utils', os.path.join(base, 'utils')),
+                       ('meltingpot.utils.substrates', os.path.join(base, 'utils', 'substrates')),
+                       ('meltingpot.utils.substrates.wrappers', os.path.join(base, 'utils', 'substrates', 'wrappers')),
+                       ('meltingpot.configs', os.path.join(base, 'configs'))):
+      module = types.ModuleType(name)
+      module.__path__ = [path]
+      sys.modules[name] = module
+    yield base
+  finally:
+    for k in [k for k in sys.modules if mine(k)]:
+      del sys.modules[k]
+    sys.modules.update(saved)
+
+
+def load_reference_config(name: str, root: Optional[str] = None):
+  """Imports `meltingpot.configs.substrates.<name>` from a reference checkout and returns its config."""
   import importlib  # pylint: disable=g-import-not-at-top
-  configs = importlib.import_module('meltingpot.configs.substrates')
-  return configs.get_config(name)
+  with reference_packages(root):
+    configs = importlib.import_module('meltingpot.configs.substrates')
+    return configs.get_config(name)
 
 
 def _plain(value: Any) -> Any:

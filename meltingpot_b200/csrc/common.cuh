@@ -21,6 +21,7 @@
 #define MP_MAX_LAYERS 16
 #define MP_MAX_BEAM_CELLS 32
 #define MP_FULL 0xffffffffu
+#define MP_MAX_PEERS 8   // ranks of one NVSwitch domain that exchange their timesteps (mp_exchange_*)
 
 enum { ENV_STEP = 0, ENV_EPISODE = 1, ENV_DONE = 2, ENV_DIRT = 3, ENV_CLEANED = 4, ENV_ATE = 5, ENV_BEAM = 6, ENV_COLS = 8 };
 enum { AV_X = 0, AV_Y = 1, AV_ORIENT = 2, AV_ALIVE = 3 };
@@ -131,6 +132,14 @@ struct State {
   int32_t* events;     // [B][max_events][3] (type, a, b) of the current step, unordered (see emit_event)
   int32_t* n_events;   // [B] events emitted this step
   int max_events;      // rows per env: the family's worst case for one step (mp_create), so nothing is ever dropped
+  // Cross-GPU exchange of the stacked timestep (mp_exchange_*, include/mp_engine.h). Off when x_world == 0. Every rank
+  // owns gathered[2][x_world * B][P + 2] and flags[MP_MAX_PEERS]; x_gathered / x_flags are those buffers of every rank,
+  // mapped into this process (NVLink peer memory; entry x_rank is the local one).
+  int x_world, x_rank;
+  unsigned long long x_step;               // sequence number of this launch; slot = x_step & 1
+  double* x_gathered[MP_MAX_PEERS];
+  unsigned long long* x_flags[MP_MAX_PEERS];
+  unsigned int* x_counter;                 // local: env warps that have published in this launch
 };
 
 // Events of the current step (the reference's events:add calls on the hot path). Types follow
@@ -182,4 +191,60 @@ __device__ __forceinline__ bool wrap_or_reject(const Tables& T, int& x, int& y) 
     return true;
   }
   return x >= 0 && x < T.W && y >= 0 && y < T.H;
+}
+
+// Called by every env warp at the end of a state-transition launch (also by envs a masked reset left untouched, so
+// that the slot of this step is complete). Lane i < P + 2 forwards element i of the env's packed timestep row
+// (reward[0..P), discount, step type) to every rank's gathered buffer with plain stores through the peer mapping:
+// the "all-gather" is P + 2 remote stores per env and rank, issued by the kernel that produced the values, with no
+// collective kernel and no extra launch. The last warp of the grid to finish raises flags[x_rank] = x_step on every
+// rank (release at system scope), which k_exchange_wait polls on the consumer side.
+__device__ __forceinline__ void exchange_publish(const Tables& T, const State& S, int b, int lane) {
+  if (S.x_world == 0) return;
+  __syncwarp();
+  // Flow control: slot (x_step & 1) still holds step x_step - 2 on every rank. A rank has finished with it (its
+  // consumers are stream-ordered before its next launch) once it has published step x_step - 1, so wait for that.
+  // The slowest rank never waits on a faster one, hence no cycle; in steady state the flags were raised a whole
+  // render ago and this is one local read.
+  if (lane < S.x_world && S.x_step > 1ull) {
+    const unsigned long long* f = S.x_flags[S.x_rank] + lane;
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v + 1ull < S.x_step) __nanosleep(100);
+    } while (v + 1ull < S.x_step);
+  }
+  __syncwarp();
+  const int n = T.P + 2;
+  if (lane < n) {
+    const double v = S.packed[(size_t)b * n + lane];
+    const size_t off = ((size_t)(S.x_step & 1ull) * S.x_world * S.B + (size_t)S.x_rank * S.B + b) * n + lane;
+    for (int r = 0; r < S.x_world; ++r) S.x_gathered[r][off] = v;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_system();  // this warp's remote stores are performed before its arrival is counted
+    const unsigned int arrived = atomicAdd(S.x_counter, 1u);
+    if (arrived == (unsigned int)S.B - 1u) {
+      __threadfence_system();
+      *S.x_counter = 0u;  // (the next launch on this engine is stream-ordered after this kernel)
+      for (int r = 0; r < S.x_world; ++r) {
+        unsigned long long* f = S.x_flags[r] + S.x_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(S.x_step) : "memory");
+      }
+    }
+  }
+}
+
+// One warp: lane r < world waits until rank r has published step `step` into this rank's gathered buffer. Small
+// enough (32 threads, no shared memory) to be resident next to a persistent k_render CTA.
+__global__ void __launch_bounds__(32) k_exchange_wait(const unsigned long long* flags, int world, unsigned long long step) {
+  const int lane = threadIdx.x;
+  if (lane < world) {
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + lane) : "memory");
+      if (v < step) __nanosleep(200);
+    } while (v < step);
+  }
 }

@@ -61,7 +61,8 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 constexpr int kRenderSmemLimit = 227 * 1024 - 2560;  // dynamic shared memory: the 227 KB opt-in maximum less k_render's static arrays
 constexpr int kMaxAtlasSprites = 96;
-#define MP_MAX_DEVICES 64  // sprites incl. pre-merged ones kept in shared memory by k_render
+#define MP_MAX_DEVICES 64
+#define MP_EXCHANGE_HEADER 256  // bytes reserved for the per-rank flags in front of the gathered rows  // sprites incl. pre-merged ones kept in shared memory by k_render
 
 // Beam footprint in visiting order (policy A.8): centre ray, then for each side the lateral cells
 // outwards, each followed by its forward ray of length `length - k`.
@@ -100,6 +101,19 @@ struct mp_engine {
   mp_buffers buffers{};
   std::vector<void*> allocs;
   int32_t* d_actions = nullptr;  // staging for mp_step_host
+  // one allocation holding reward | discount | step_type | scalar_obs, so the host path moves them with one copy
+  uint8_t* scalar_block = nullptr;
+  size_t scalar_block_bytes = 0;
+  // mp_step_host_async: two slots, each with its own observation images, action staging and scalar staging
+  struct AsyncSlot { uint8_t* rgb = nullptr; uint8_t* world_rgb = nullptr; int32_t* actions = nullptr; uint8_t* scalars = nullptr;
+                     cudaEvent_t computed = nullptr, copied = nullptr; };
+  AsyncSlot slot[2];
+  cudaStream_t copy_stream = nullptr;
+  bool async_ready = false;
+  // mp_exchange_*: this rank's gathered / flags buffers and the launch sequence number
+  uint8_t* x_block = nullptr;      // [flags: MP_EXCHANGE_HEADER bytes][gathered f64 [2][world * B][P + 2]]
+  uint64_t x_block_bytes = 0;
+  unsigned long long x_seq = 0;   // incremented by every state-transition launch once the exchange is connected
   int32_t* d_avatar_dbg = nullptr;
   uint64_t launches = 0;
   int sm_count = 0;
@@ -578,6 +592,7 @@ int build_plan(mp_engine* E) {
 
 int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int mode, cudaStream_t st) {
   const int blocks = (E->B + 3) / 4;
+  if (E->S.x_world) E->S.x_step = ++E->x_seq;
   if (E->family == MPB_FAMILY_CLEAN_UP) k_step_clean_up<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
   else if (E->family == MPB_FAMILY_COMMONS_HARVEST) k_step_commons<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
   else if (E->family == MPB_FAMILY_COINS) k_step_coins<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
@@ -611,6 +626,10 @@ int copy_out(mp_engine* E, const mp_host_outputs* out, cudaStream_t st) {
   const size_t B = E->B, P = E->T.P;
   if (out->rgb) CUDA_TRY(cudaMemcpyAsync(out->rgb, bf.rgb, B * P * E->R.player_bytes, cudaMemcpyDeviceToHost, st));
   if (out->world_rgb) CUDA_TRY(cudaMemcpyAsync(out->world_rgb, bf.world_rgb, B * E->R.world_bytes, cudaMemcpyDeviceToHost, st));
+  if (out->scalar_block) {  // reward | discount | step_type | scalar_obs in one transfer (layout of mp_buffers.scalar_block)
+    CUDA_TRY(cudaMemcpyAsync(out->scalar_block, E->scalar_block, E->scalar_block_bytes, cudaMemcpyDeviceToHost, st));
+    return MP_OK;
+  }
   if (out->reward) CUDA_TRY(cudaMemcpyAsync(out->reward, bf.reward, B * P * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (out->discount) CUDA_TRY(cudaMemcpyAsync(out->discount, bf.discount, B * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (out->step_type) CUDA_TRY(cudaMemcpyAsync(out->step_type, bf.step_type, B * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -665,13 +684,20 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   S.fam_u8_stride = std::max(16, RU_COUNT * T.nR_pad); S.fam_u16_stride = std::max(16, RS_COUNT * T.nR_pad);
   if ((rc = E->alloc(B * T.L * T.cells_pad, &S.grid)) || (rc = E->alloc(B * P * 4, &S.avatar)) || (rc = E->alloc(B * P * 4, &S.av_timer)) ||
       (rc = E->alloc(B * T.nA_pad, &S.apple)) || (rc = E->alloc(B * T.nD_pad, &S.dirt)) || (rc = E->alloc(B * T.nW_pad, &S.water)) || (rc = E->alloc(B * T.nA_pad, &S.apple_count)) || (rc = E->alloc(B * (size_t)S.fam_u8_stride, &S.fam_u8)) || (rc = E->alloc(B * (size_t)S.fam_u16_stride, &S.fam_u16)) || (rc = E->alloc(B * P * 8, &S.av_extra)) || (rc = E->alloc(B * (P + 2), &S.packed)) ||
-      (rc = E->alloc(B * ENV_COLS, &S.env)) || (rc = E->alloc(B * P, &S.reward)) || (rc = E->alloc(B, &S.discount)) ||
-      (rc = E->alloc(B, &S.step_type)) || (rc = E->alloc(std::max<size_t>(1, T.n_scalar) * B * P, &S.scalar_obs)) ||
+      (rc = E->alloc(B * ENV_COLS, &S.env)) ||
+      (rc = E->alloc((B * P + B + B + std::max<size_t>(1, T.n_scalar) * B * P) * 8, &E->scalar_block)) ||
       (rc = E->alloc(B * P * E->R.player_bytes, &S.rgb)) || (rc = E->alloc(B * (size_t)E->R.world_bytes, &S.world_rgb)) ||
       (rc = E->alloc(B * (size_t)S.max_events * 3, &S.events)) || (rc = E->alloc(B, &S.n_events)) ||
       (rc = E->alloc(B * P, &E->d_actions))) {
     mp_destroy(E);
     return rc;
+  }
+  {  // reward [B][P] | discount [B] | step_type [B] | scalar_obs [n][B][P], all 8-byte elements, one block
+    E->scalar_block_bytes = (B * P + B + B + std::max<size_t>(1, T.n_scalar) * B * P) * 8;
+    S.reward = reinterpret_cast<double*>(E->scalar_block);
+    S.discount = S.reward + B * P;
+    S.step_type = reinterpret_cast<int64_t*>(S.discount + B);
+    S.scalar_obs = reinterpret_cast<double*>(S.step_type + B);
   }
   {  // everything a later step depends on, plus the current timestep scalars; the images are re-rendered on load
     const size_t ns = std::max<size_t>(1, T.n_scalar);
@@ -725,6 +751,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   bf.scalar_obs = S.scalar_obs; bf.avatar_state = S.avatar; bf.grid = S.grid; bf.timestep_packed = S.packed;
   bf.grid_layers = T.L; bf.grid_cells = T.cells; bf.grid_cells_padded = T.cells_pad;
   bf.events = S.events; bf.event_count = S.n_events; bf.max_events = S.max_events;
+  bf.scalar_block = E->scalar_block; bf.scalar_block_bytes = E->scalar_block_bytes;
   // observations + scalars + actions + one read and one write of the compact grid.
   E->render_bytes = (uint64_t)P * E->R.player_bytes + (uint64_t)E->R.world_bytes + (uint64_t)T.L * T.cells * 2;
   E->algo_bytes = (uint64_t)P * E->R.player_bytes + (uint64_t)E->R.world_bytes + 8ull * ((1 + T.n_scalar) * P + 2) + 8ull * P + 2ull * T.L * T.cells * 2;
@@ -737,6 +764,8 @@ int mp_destroy(mp_handle h) {
   {
     DeviceGuard guard(h->device);
     cudaDeviceSynchronize();
+    for (auto& sl : h->slot) { if (sl.computed) cudaEventDestroy(sl.computed); if (sl.copied) cudaEventDestroy(sl.copied); }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (void* p : h->allocs) cudaFree(p);
   }
   delete h;
@@ -801,6 +830,162 @@ int mp_reset_host(mp_handle h, const mp_host_outputs* out, void* stream) {
   if (!rc) rc = copy_out(h, out, st);
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(st));
+  return MP_OK;
+}
+
+namespace {
+// Lazily sets up the two slots of mp_step_host_async. Slot 0 renders into the engine's own images (mp_buffers.rgb /
+// world_rgb); slot 1 gets a second set, so the kernels of one step can run while the previous step's images are
+// still being copied out.
+int async_setup(mp_engine* E) {
+  if (E->async_ready) return MP_OK;
+  const size_t B = E->B, P = E->T.P;
+  int rc;
+  E->slot[0].rgb = E->S.rgb; E->slot[0].world_rgb = E->S.world_rgb;
+  if ((rc = E->alloc(B * P * E->R.player_bytes, &E->slot[1].rgb)) || (rc = E->alloc(B * (size_t)E->R.world_bytes, &E->slot[1].world_rgb))) return rc;
+  for (auto& sl : E->slot) {
+    if ((rc = E->alloc(B * P, &sl.actions)) || (rc = E->alloc(E->scalar_block_bytes, &sl.scalars))) return rc;
+    CUDA_TRY(cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
+  E->async_ready = true;
+  return MP_OK;
+}
+}  // namespace
+
+int mp_step_host_async(mp_handle h, const int32_t* actions_host, const mp_host_outputs* out, int slot, void* stream) {
+  if (!h || !actions_host || slot < 0 || slot > 1) return fail(MP_E_INVALID, "mp_step_host_async: null handle / actions or slot outside 0..1");
+  DeviceGuard guard(h->device);
+  int rc = async_setup(h);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  mp_engine::AsyncSlot& sl = h->slot[slot];
+  CUDA_TRY(cudaStreamWaitEvent(st, sl.copied, 0));  // the copy-out that last used this slot's device buffers has drained
+  CUDA_TRY(cudaMemcpyAsync(sl.actions, actions_host, (size_t)h->B * h->T.P * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if ((rc = launch_state(h, sl.actions, nullptr, 0, st))) return rc;
+  uint8_t* rgb0 = h->S.rgb; uint8_t* world0 = h->S.world_rgb;
+  h->S.rgb = sl.rgb; h->S.world_rgb = sl.world_rgb;
+  rc = launch_render(h, st);
+  h->S.rgb = rgb0; h->S.world_rgb = world0;
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(sl.scalars, h->scalar_block, h->scalar_block_bytes, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaEventRecord(sl.computed, st));
+  CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, sl.computed, 0));
+  if (out) {
+    const size_t B = h->B, P = h->T.P;
+    cudaStream_t cs = h->copy_stream;
+    if (out->rgb) CUDA_TRY(cudaMemcpyAsync(out->rgb, sl.rgb, B * P * h->R.player_bytes, cudaMemcpyDeviceToHost, cs));
+    if (out->world_rgb) CUDA_TRY(cudaMemcpyAsync(out->world_rgb, sl.world_rgb, B * h->R.world_bytes, cudaMemcpyDeviceToHost, cs));
+    if (out->scalar_block) CUDA_TRY(cudaMemcpyAsync(out->scalar_block, sl.scalars, h->scalar_block_bytes, cudaMemcpyDeviceToHost, cs));
+    else {
+      const uint8_t* sb = sl.scalars;
+      if (out->reward) CUDA_TRY(cudaMemcpyAsync(out->reward, sb, B * P * 8, cudaMemcpyDeviceToHost, cs));
+      if (out->discount) CUDA_TRY(cudaMemcpyAsync(out->discount, sb + B * P * 8, B * 8, cudaMemcpyDeviceToHost, cs));
+      if (out->step_type) CUDA_TRY(cudaMemcpyAsync(out->step_type, sb + (B * P + B) * 8, B * 8, cudaMemcpyDeviceToHost, cs));
+      if (out->scalar_obs && h->T.n_scalar) CUDA_TRY(cudaMemcpyAsync(out->scalar_obs, sb + (B * P + 2 * B) * 8, (size_t)h->T.n_scalar * B * P * 8, cudaMemcpyDeviceToHost, cs));
+    }
+  }
+  CUDA_TRY(cudaEventRecord(sl.copied, h->copy_stream));
+  return MP_OK;
+}
+
+int mp_wait(mp_handle h, int slot) {
+  if (!h || slot < 0 || slot > 1) return fail(MP_E_INVALID, "mp_wait: null handle or slot outside 0..1");
+  if (!h->async_ready) return MP_OK;
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaEventSynchronize(h->slot[slot].copied));
+  return MP_OK;
+}
+
+// ---- cross-GPU exchange of the stacked timestep ---------------------------------------------------------------------
+int mp_exchange_create(mp_handle h, int rank, int world, void** block, uint64_t* block_bytes) {
+  if (!h || world < 1 || world > MP_MAX_PEERS || rank < 0 || rank >= world) return fail(MP_E_INVALID, "mp_exchange_create: rank %d / world %d (max %d ranks)", rank, world, MP_MAX_PEERS);
+  if (h->x_block) return fail(MP_E_INVALID, "mp_exchange_create: already created for this handle");
+  DeviceGuard guard(h->device);
+  const size_t n = (size_t)2 * world * h->B * (h->T.P + 2);
+  int rc;
+  // one allocation: flags (MP_EXCHANGE_HEADER bytes) then gathered, so that one IPC handle shares both
+  if ((rc = h->alloc(MP_EXCHANGE_HEADER + n * sizeof(double), &h->x_block)) || (rc = h->alloc((size_t)4, &h->S.x_counter))) return rc;
+  h->x_block_bytes = MP_EXCHANGE_HEADER + n * sizeof(double);
+  h->S.x_rank = rank;  // x_world stays 0 (exchange off) until mp_exchange_connect
+  h->buffers.gathered = reinterpret_cast<double*>(h->x_block + MP_EXCHANGE_HEADER); h->buffers.gathered_world = world;
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (block) *block = h->x_block;
+  if (block_bytes) *block_bytes = h->x_block_bytes;
+  return MP_OK;
+}
+
+int mp_ipc_export(const void* device_ptr, void* handle64, uint64_t* offset) {
+  if (!device_ptr || !handle64 || !offset) return fail(MP_E_INVALID, "mp_ipc_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t hd;
+  CUDA_TRY(cudaIpcGetMemHandle(&hd, const_cast<void*>(device_ptr)));
+  memcpy(handle64, &hd, sizeof hd);
+  // The handle names the driver allocation that contains the pointer (cudaMalloc sub-allocates small requests), and
+  // opening it yields that allocation's base: the receiver needs the pointer's offset from the base as well.
+  typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+  if (!fn || qr != cudaDriverEntryPointSuccess) return fail(MP_E_CUDA, "cuMemGetAddressRange is not available");
+  unsigned long long base = 0; size_t size = 0;
+  if (reinterpret_cast<GetRange>(fn)(&base, &size, (unsigned long long)(uintptr_t)device_ptr) != 0) return fail(MP_E_CUDA, "cuMemGetAddressRange failed");
+  *offset = (uint64_t)((unsigned long long)(uintptr_t)device_ptr - base);
+  return MP_OK;
+}
+
+int mp_ipc_open(int device, const void* handle64, uint64_t offset, void** device_ptr) {
+  if (!handle64 || !device_ptr) return fail(MP_E_INVALID, "mp_ipc_open: null argument");
+  DeviceGuard guard(device);
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, sizeof hd);
+  void* base = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+  *device_ptr = static_cast<uint8_t*>(base) + offset;
+  return MP_OK;
+}
+
+int mp_enable_peer_access(int device, int peer_device) {
+  if (device == peer_device) return MP_OK;
+  DeviceGuard guard(device);
+  int can = 0;
+  CUDA_TRY(cudaDeviceCanAccessPeer(&can, device, peer_device));
+  if (!can) return fail(MP_E_UNSUPPORTED, "device %d cannot access device %d (no NVLink / P2P path)", device, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return MP_OK; }
+  CUDA_TRY(e);
+  return MP_OK;
+}
+
+int mp_exchange_connect(mp_handle h, void* const* peer_blocks) {
+  if (!h || !peer_blocks) return fail(MP_E_INVALID, "mp_exchange_connect: null argument");
+  if (!h->x_block) return fail(MP_E_INVALID, "mp_exchange_connect: call mp_exchange_create first");
+  const int world = h->buffers.gathered_world;
+  if (peer_blocks[h->S.x_rank] != h->x_block) return fail(MP_E_INVALID, "mp_exchange_connect: entry %d must be this rank's own block", h->S.x_rank);
+  for (int r = 0; r < world; ++r) {
+    if (!peer_blocks[r]) return fail(MP_E_INVALID, "mp_exchange_connect: null pointer for rank %d", r);
+    h->S.x_flags[r] = static_cast<unsigned long long*>(peer_blocks[r]);
+    h->S.x_gathered[r] = reinterpret_cast<double*>(static_cast<uint8_t*>(peer_blocks[r]) + MP_EXCHANGE_HEADER);
+  }
+  h->S.x_world = world;
+  return MP_OK;
+}
+
+int mp_exchange_wait(mp_handle h, void* stream) {
+  if (!h) return fail(MP_E_INVALID, "null handle");
+  if (!h->S.x_world) return fail(MP_E_INVALID, "mp_exchange_wait: exchange not connected");
+  DeviceGuard guard(h->device);
+  k_exchange_wait<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(h->x_block), h->S.x_world, h->x_seq);
+  ++h->launches;
+  CUDA_TRY(cudaGetLastError());
+  return MP_OK;
+}
+
+int mp_exchange_slot(mp_handle h, int* slot, uint64_t* step) {
+  if (!h) return fail(MP_E_INVALID, "null handle");
+  if (slot) *slot = (int)(h->x_seq & 1ull);
+  if (step) *step = h->x_seq;
   return MP_OK;
 }
 

@@ -230,13 +230,11 @@ __global__ void __launch_bounds__(128) k_step_coins(Tables T, State S, const int
   const int b = blockIdx.x * 4 + warp;
   if (b >= S.B) return;
   WarpScratch sc = carve_scratch(T, smem + warp * warp_scratch_bytes(T));
-  if (mode == 1 && !(mask == nullptr || mask[b])) return;
-  if (lane == 0) S.n_events[b] = 0;
-  __syncwarp();
-  if (mode == 1) {
-    coins_reset(T, S, b, lane, sc);
-    return;
+  if (!(mode == 1 && !(mask == nullptr || mask[b]))) {
+    if (lane == 0) S.n_events[b] = 0;
+    __syncwarp();
+    if (mode == 1 || S.env[(size_t)b * ENV_COLS + ENV_DONE]) coins_reset(T, S, b, lane, sc);
+    else coins_step(T, S, b, lane, actions, sc);
   }
-  if (S.env[(size_t)b * ENV_COLS + ENV_DONE]) coins_reset(T, S, b, lane, sc);
-  else coins_step(T, S, b, lane, actions, sc);
+  exchange_publish(T, S, b, lane);
 }

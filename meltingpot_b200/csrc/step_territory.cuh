@@ -429,17 +429,19 @@ __global__ void __launch_bounds__(128) k_step_territory(Tables T, State S, const
   const uint64_t key = S.seed + (uint64_t)b;
   const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
   const bool reset = mode == 1 ? (mask == nullptr || mask[b]) : (env[ENV_DONE] != 0);
-  if (mode == 1 && !reset) return;
-  if (lane == 0) S.n_events[b] = 0;
-  __syncwarp();
-  if (reset) {
-    const int episode = env[ENV_EPISODE] + 1;
+  if (!(mode == 1 && !reset)) {
+    if (lane == 0) S.n_events[b] = 0;
     __syncwarp();
-    territory_init(T, S, b, lane, sc, episode, k0, k1);
-    if (lane == 0) { env[ENV_EPISODE] = episode; env[ENV_BEAM] = 0; }
-    __syncwarp();
-    territory_frame(T, S, b, lane, nullptr, sc, 0, episode, k0, k1);
-  } else {
-    territory_frame(T, S, b, lane, actions, sc, env[ENV_STEP] + 1, env[ENV_EPISODE], k0, k1);
+    if (reset) {
+      const int episode = env[ENV_EPISODE] + 1;
+      __syncwarp();
+      territory_init(T, S, b, lane, sc, episode, k0, k1);
+      if (lane == 0) { env[ENV_EPISODE] = episode; env[ENV_BEAM] = 0; }
+      __syncwarp();
+      territory_frame(T, S, b, lane, nullptr, sc, 0, episode, k0, k1);
+    } else {
+      territory_frame(T, S, b, lane, actions, sc, env[ENV_STEP] + 1, env[ENV_EPISODE], k0, k1);
+    }
   }
+  exchange_publish(T, S, b, lane);
 }

@@ -54,6 +54,25 @@ def gather_timestep_scalars(reward, discount, step_type, group=None):
   return full[:, :p], full[:, p], full[:, p + 1].to(torch.int64)
 
 
+def connect_exchange(eng, group=None) -> None:
+  """Wires `eng` (this rank's engine.Engine) into the cross-GPU timestep exchange (mp_exchange_*).
+
+  torch.distributed only carries the 64-byte CUDA IPC handles between the ranks, once; from then on every
+  state-transition kernel writes its packed timestep rows straight into every rank's `gathered` buffer over
+  NVLink peer mappings, with no collective kernel per step.
+  """
+  import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+  from meltingpot_b200 import engine as engine_lib  # pylint: disable=g-import-not-at-top
+  rank, world = dist.get_rank(group), dist.get_world_size(group)
+  ptr, _ = eng.exchange_create(rank, world)
+  mine = engine_lib.ipc_export(ptr)
+  everyone = [None] * world
+  dist.all_gather_object(everyone, mine, group=group)
+  blocks = [ptr if r == rank else engine_lib.ipc_open(eng.device, everyone[r][0], everyone[r][1]) for r in range(world)]
+  eng.exchange_connect(blocks)
+  dist.barrier(group=group)  # nobody publishes before everyone is mapped
+
+
 class ShardedSubstrate:
   """One rank's shard of a globally indexed batch of env instances."""
 

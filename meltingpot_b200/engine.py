@@ -24,6 +24,8 @@ EXPORTED_SYMBOLS = (
     'mp_create', 'mp_destroy', 'mp_set_flags', 'mp_reset', 'mp_step',
     'mp_step_state', 'mp_render', 'mp_get_buffers', 'mp_step_host',
     'mp_reset_host', 'mp_launch_count', 'mp_algorithmic_bytes', 'mp_debug_render_tables', 'mp_debug_render_plan', 'mp_state_size', 'mp_state_save', 'mp_state_load',
+    'mp_step_host_async', 'mp_wait', 'mp_exchange_create', 'mp_ipc_export', 'mp_ipc_open', 'mp_enable_peer_access',
+    'mp_exchange_connect', 'mp_exchange_wait', 'mp_exchange_slot',
     'mp_last_error', 'mp_version',
 )
 
@@ -42,6 +44,8 @@ class MpBuffers(ctypes.Structure):
       ('grid_cells_padded', ctypes.c_int32),
       ('timestep_packed', ctypes.c_void_p),
       ('events', ctypes.c_void_p), ('event_count', ctypes.c_void_p), ('max_events', ctypes.c_int32),
+      ('scalar_block', ctypes.c_void_p), ('scalar_block_bytes', ctypes.c_uint64),
+      ('gathered', ctypes.c_void_p), ('gathered_world', ctypes.c_int32),
   ]
 
 
@@ -50,6 +54,7 @@ class MpHostOutputs(ctypes.Structure):
       ('rgb', ctypes.c_void_p), ('world_rgb', ctypes.c_void_p),
       ('reward', ctypes.c_void_p), ('discount', ctypes.c_void_p),
       ('step_type', ctypes.c_void_p), ('scalar_obs', ctypes.c_void_p),
+      ('scalar_block', ctypes.c_void_p),
   ]
 
 
@@ -87,6 +92,15 @@ def load_library() -> ctypes.CDLL:
   lib.mp_state_load.argtypes = [vp, vp, ctypes.c_uint64, vp]
   lib.mp_debug_render_plan.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
   lib.mp_debug_render_tables.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), vp, vp]
+  lib.mp_step_host_async.argtypes = [vp, vp, ctypes.POINTER(MpHostOutputs), ctypes.c_int, vp]
+  lib.mp_wait.argtypes = [vp, ctypes.c_int]
+  lib.mp_exchange_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_uint64)]
+  lib.mp_ipc_export.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_uint64)]
+  lib.mp_ipc_open.argtypes = [ctypes.c_int, vp, ctypes.c_uint64, ctypes.POINTER(vp)]
+  lib.mp_enable_peer_access.argtypes = [ctypes.c_int, ctypes.c_int]
+  lib.mp_exchange_connect.argtypes = [vp, ctypes.POINTER(vp)]
+  lib.mp_exchange_wait.argtypes = [vp, vp]
+  lib.mp_exchange_slot.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint64)]
   lib.mp_last_error.restype = ctypes.c_char_p
   lib.mp_version.restype = ctypes.c_char_p
   _lib = lib
@@ -192,7 +206,7 @@ class Engine:
 
   # -- lifecycle -----------------------------------------------------------------
   _VIEWS = ('rgb', 'world_rgb', 'reward', 'discount', 'step_type', 'scalar_obs', 'avatar_state', 'grid',
-            'timestep_packed', 'events', 'event_count')
+            'timestep_packed', 'events', 'event_count', 'gathered')
 
   def close(self) -> None:
     """Drops this object's references. mp_destroy runs when the last tensor view handed out has been released too
@@ -246,16 +260,24 @@ class Engine:
 
   # -- host-buffer API (end-to-end path) -----------------------------------------
   def make_host_outputs(self, rgb=True, world_rgb=True) -> Dict[str, 'np.ndarray']:
-    """Pinned host tensors for mp_step_host, as a dict of torch CPU tensors."""
+    """Pinned host tensors for mp_step_host / mp_step_host_async, as a dict of torch CPU tensors.
+
+    reward / discount / step_type / scalar_obs are views of one pinned block laid out like mp_buffers.scalar_block,
+    so the engine moves all scalar outputs of a step with a single device->host copy.
+    """
     torch = self._torch
     b = self.buffers
     B, P = self.num_envs, self.num_players
-    out = {
-        'reward': torch.empty((B, P), dtype=torch.float64).pin_memory(),
-        'discount': torch.empty((B,), dtype=torch.float64).pin_memory(),
-        'step_type': torch.empty((B,), dtype=torch.int64).pin_memory(),
-        'scalar_obs': torch.empty((max(self.num_scalar_obs, 1), B, P), dtype=torch.float64).pin_memory(),
-    }
+    ns = max(self.num_scalar_obs, 1)
+    n_words = int(b.scalar_block_bytes) // 8
+    assert n_words == B * P + 2 * B + ns * B * P
+    block = torch.empty((n_words,), dtype=torch.float64).pin_memory()
+    o = 0
+    out = {'scalar_block': block}
+    out['reward'] = block[o:o + B * P].view(B, P); o += B * P
+    out['discount'] = block[o:o + B]; o += B
+    out['step_type'] = block[o:o + B].view(torch.int64); o += B
+    out['scalar_obs'] = block[o:o + ns * B * P].view(ns, B, P)
     if rgb:
       out['rgb'] = torch.empty((B, P, b.rgb_h, b.rgb_w, 3), dtype=torch.uint8).pin_memory()
     if world_rgb:
@@ -265,7 +287,7 @@ class Engine:
   @staticmethod
   def _host_struct(outputs) -> MpHostOutputs:
     s = MpHostOutputs()
-    for name in ('rgb', 'world_rgb', 'reward', 'discount', 'step_type', 'scalar_obs'):
+    for name in ('rgb', 'world_rgb', 'reward', 'discount', 'step_type', 'scalar_obs', 'scalar_block'):
       t = outputs.get(name) if outputs else None
       setattr(s, name, ctypes.c_void_p(t.data_ptr()) if t is not None else None)
     return s
@@ -277,6 +299,50 @@ class Engine:
     s = self._host_struct(outputs)
     _check(self._lib.mp_step_host(self._h, ctypes.c_void_p(actions_host.data_ptr()),
                                   ctypes.byref(s), self._stream(stream)))
+
+  def step_host_async(self, actions_host, outputs, slot: int, stream=None) -> None:
+    """Pipelined step (mp_step_host_async): returns at once; `wait(slot)` before reading `outputs` or reusing
+    `actions_host`. Alternate slot 0 / 1 between consecutive calls."""
+    assert actions_host.dtype == self._torch.int32 and not actions_host.is_cuda
+    assert actions_host.is_contiguous() and actions_host.shape == (self.num_envs, self.num_players)
+    s = self._host_struct(outputs)
+    _check(self._lib.mp_step_host_async(self._h, ctypes.c_void_p(actions_host.data_ptr()), ctypes.byref(s),
+                                        int(slot), self._stream(stream)))
+
+  def wait(self, slot: int) -> None:
+    _check(self._lib.mp_wait(self._h, int(slot)))
+
+  # -- stacked timestep across GPUs (mp_exchange_*) ------------------------------------
+  def exchange_create(self, rank: int, world: int):
+    """Allocates this rank's exchange block; returns (device pointer, bytes)."""
+    ptr, n = ctypes.c_void_p(), ctypes.c_uint64(0)
+    _check(self._lib.mp_exchange_create(self._h, int(rank), int(world), ctypes.byref(ptr), ctypes.byref(n)))
+    self._x_world, self._x_rank = int(world), int(rank)
+    bufs = MpBuffers()
+    _check(self._lib.mp_get_buffers(self._h, ctypes.byref(bufs)))
+    self.buffers = bufs
+    torch = self._torch
+    self.gathered = torch.as_tensor(
+        _CudaView(bufs.gathered, (2, world * self.num_envs, self.num_players + 2), '<f8', self._owner),
+        device=torch.device('cuda', self.device), dtype=torch.float64)
+    return int(ptr.value), int(n.value)
+
+  def exchange_connect(self, peer_blocks) -> None:
+    """peer_blocks: every rank's block pointer (ints) as mapped into this process, in rank order."""
+    arr = (ctypes.c_void_p * len(peer_blocks))(*[ctypes.c_void_p(int(p)) for p in peer_blocks])
+    _check(self._lib.mp_exchange_connect(self._h, arr))
+
+  def exchange_wait(self, stream=None) -> None:
+    _check(self._lib.mp_exchange_wait(self._h, self._stream(stream)))
+
+  def exchange_slot(self):
+    slot, step = ctypes.c_int(0), ctypes.c_uint64(0)
+    _check(self._lib.mp_exchange_slot(self._h, ctypes.byref(slot), ctypes.byref(step)))
+    return int(slot.value), int(step.value)
+
+  def gathered_timestep(self):
+    """The stacked [world * B, P + 2] timestep rows of the most recent step (call exchange_wait first)."""
+    return self.gathered[self.exchange_slot()[0]]
 
   def reset_host(self, outputs, stream=None) -> None:
     s = self._host_struct(outputs)
@@ -322,3 +388,22 @@ class Engine:
     a, r = ctypes.c_uint64(0), ctypes.c_uint64(0)
     _check(self._lib.mp_algorithmic_bytes(self._h, ctypes.byref(a), ctypes.byref(r)))
     return int(a.value), int(r.value)
+
+
+def ipc_export(device_ptr: int):
+  """(64-byte CUDA IPC handle, offset) naming `device_ptr` for another process (mp_ipc_export)."""
+  handle = ctypes.create_string_buffer(64)
+  off = ctypes.c_uint64(0)
+  _check(load_library().mp_ipc_export(ctypes.c_void_p(int(device_ptr)), handle, ctypes.byref(off)))
+  return handle.raw, int(off.value)
+
+
+def ipc_open(device: int, handle: bytes, offset: int) -> int:
+  ptr = ctypes.c_void_p()
+  buf = ctypes.create_string_buffer(bytes(handle), 64)
+  _check(load_library().mp_ipc_open(int(device), buf, ctypes.c_uint64(int(offset)), ctypes.byref(ptr)))
+  return int(ptr.value)
+
+
+def enable_peer_access(device: int, peer_device: int) -> None:
+  _check(load_library().mp_enable_peer_access(int(device), int(peer_device)))

@@ -5,6 +5,8 @@ what the substrate compiler must reproduce from the reference's own Python data:
 observation names and specs, the ASCII-map census, palette arithmetic (shapes.get_palette /
 scale_color) and the sprite pixels the reference's shapes + palettes produce.
 """
+import os
+os.environ.setdefault('MELTINGPOT_REFERENCE_ROOT', '/root/reference')  # this tool runs where the checkout is
 import hashlib
 import json
 import os

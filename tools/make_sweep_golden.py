@@ -7,6 +7,8 @@ GPU box has none). Substrates with build-time randomness use substrates.BUILD_SE
 
   python tools/make_sweep_golden.py
 """
+import os
+os.environ.setdefault('MELTINGPOT_REFERENCE_ROOT', '/root/reference')  # this tool runs where the checkout is
 import hashlib
 import json
 import os

@@ -6,6 +6,8 @@ exercises AppleGrow / Edible / double-entry edge cases that a random policy on t
 whose river only gets dirtier, never reaches.
 """
 import os
+os.environ.setdefault('MELTINGPOT_REFERENCE_ROOT', '/root/reference')  # this tool runs where the checkout is
+import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
