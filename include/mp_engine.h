@@ -130,6 +130,8 @@ typedef struct mp_host_outputs {
   double* scalar_obs;
   void* scalar_block; /* if non-NULL: receives mp_buffers.scalar_block (scalar_block_bytes bytes) in one transfer and the
                          four scalar pointers above are ignored */
+  int32_t* events;      /* i32 [B][max_events][3], or NULL */
+  int32_t* event_count; /* i32 [B], or NULL */
 } mp_host_outputs;
 int mp_step_host(mp_handle h, const int32_t* actions_host, const mp_host_outputs* out, void* stream);
 int mp_reset_host(mp_handle h, const mp_host_outputs* out, void* stream);

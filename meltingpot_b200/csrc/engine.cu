@@ -626,6 +626,8 @@ int copy_out(mp_engine* E, const mp_host_outputs* out, cudaStream_t st) {
   const size_t B = E->B, P = E->T.P;
   if (out->rgb) CUDA_TRY(cudaMemcpyAsync(out->rgb, bf.rgb, B * P * E->R.player_bytes, cudaMemcpyDeviceToHost, st));
   if (out->world_rgb) CUDA_TRY(cudaMemcpyAsync(out->world_rgb, bf.world_rgb, B * E->R.world_bytes, cudaMemcpyDeviceToHost, st));
+  if (out->events) CUDA_TRY(cudaMemcpyAsync(out->events, bf.events, B * (size_t)bf.max_events * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (out->event_count) CUDA_TRY(cudaMemcpyAsync(out->event_count, bf.event_count, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (out->scalar_block) {  // reward | discount | step_type | scalar_obs in one transfer (layout of mp_buffers.scalar_block)
     CUDA_TRY(cudaMemcpyAsync(out->scalar_block, E->scalar_block, E->scalar_block_bytes, cudaMemcpyDeviceToHost, st));
     return MP_OK;
@@ -872,6 +874,7 @@ int mp_step_host_async(mp_handle h, const int32_t* actions_host, const mp_host_o
   CUDA_TRY(cudaMemcpyAsync(sl.scalars, h->scalar_block, h->scalar_block_bytes, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaEventRecord(sl.computed, st));
   CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, sl.computed, 0));
+  if (out && (out->events || out->event_count)) return fail(MP_E_INVALID, "mp_step_host_async: events are not staged per slot; read them with mp_step_host");
   if (out) {
     const size_t B = h->B, P = h->T.P;
     cudaStream_t cs = h->copy_stream;

@@ -54,7 +54,7 @@ class MpHostOutputs(ctypes.Structure):
       ('rgb', ctypes.c_void_p), ('world_rgb', ctypes.c_void_p),
       ('reward', ctypes.c_void_p), ('discount', ctypes.c_void_p),
       ('step_type', ctypes.c_void_p), ('scalar_obs', ctypes.c_void_p),
-      ('scalar_block', ctypes.c_void_p),
+      ('scalar_block', ctypes.c_void_p), ('events', ctypes.c_void_p), ('event_count', ctypes.c_void_p),
   ]
 
 
@@ -259,7 +259,7 @@ class Engine:
       raise ValueError('actions must be a contiguous int32 CUDA tensor [B, P] on the engine device')
 
   # -- host-buffer API (end-to-end path) -----------------------------------------
-  def make_host_outputs(self, rgb=True, world_rgb=True) -> Dict[str, 'np.ndarray']:
+  def make_host_outputs(self, rgb=True, world_rgb=True, events=False) -> Dict[str, 'np.ndarray']:
     """Pinned host tensors for mp_step_host / mp_step_host_async, as a dict of torch CPU tensors.
 
     reward / discount / step_type / scalar_obs are views of one pinned block laid out like mp_buffers.scalar_block,
@@ -282,12 +282,15 @@ class Engine:
       out['rgb'] = torch.empty((B, P, b.rgb_h, b.rgb_w, 3), dtype=torch.uint8).pin_memory()
     if world_rgb:
       out['world_rgb'] = torch.empty((B, b.world_h, b.world_w, 3), dtype=torch.uint8).pin_memory()
+    if events:
+      out['events'] = torch.empty((B, b.max_events, 3), dtype=torch.int32).pin_memory()
+      out['event_count'] = torch.empty((B,), dtype=torch.int32).pin_memory()
     return out
 
   @staticmethod
   def _host_struct(outputs) -> MpHostOutputs:
     s = MpHostOutputs()
-    for name in ('rgb', 'world_rgb', 'reward', 'discount', 'step_type', 'scalar_obs', 'scalar_block'):
+    for name in ('rgb', 'world_rgb', 'reward', 'discount', 'step_type', 'scalar_obs', 'scalar_block', 'events', 'event_count'):
       t = outputs.get(name) if outputs else None
       setattr(s, name, ctypes.c_void_p(t.data_ptr()) if t is not None else None)
     return s

@@ -220,32 +220,50 @@ class Substrate(dm_env.Environment):
                                              events=self._events_subject)
     self._closed = False
     self._last_observation = None
+    self._last_events = np.zeros((0, 3), np.int32)
+    self._host = None
 
   # -- helpers --------------------------------------------------------------------------------
-  def _to_timestep(self, bts: BatchedTimeStep) -> dm_env.TimeStep:
-    self._torch.cuda.synchronize(self._batched.engine.device)
-    step_type = dm_env.StepType(int(bts.step_type[0].item()))
-    reward_np = bts.reward[0].cpu().numpy()
-    rewards = [np.float64(r) for r in reward_np]
-    shared = {name: bts.observation[name][0].cpu().numpy() for name in self._global}
-    per_player = {name: bts.observation[name][0].cpu().numpy() for name in self._individual}
+  def _host_buffers(self):
+    """Pinned host buffers of the B = 1 view: one host-buffer C-ABI call per step fills them (three device->host
+    copies: images, WORLD.RGB, and the packed scalar block; plus the events), then the stream is synchronised once."""
+    if self._host is None:
+      eng = self._batched.engine
+      self._host = eng.make_host_outputs(rgb=True, world_rgb=self._batched._world_rgb, events=True)  # pylint: disable=protected-access
+      self._host_actions = self._torch.zeros((1, self._num_players), dtype=self._torch.int32).pin_memory()
+      self._scalar_index = {name: k for k, name in enumerate(self._batched._scalar_names)}  # pylint: disable=protected-access
+    return self._host
+
+  def _to_timestep(self) -> dm_env.TimeStep:
+    host = self._host
+    step_type = dm_env.StepType(int(host['step_type'][0]))
+    rewards = [np.float64(r) for r in host['reward'][0].numpy()]
+    # fresh arrays every step, as the reference returns (the pinned buffers are overwritten by the next call)
+    rgb = host['rgb'][0].numpy().copy()
+    shared = {}
+    for name in self._global:
+      shared[name] = host['world_rgb'][0].numpy().copy()
     collective = np.sum(rewards)
     observations = []
     for i in range(self._num_players):
       obs = {_COLLECTIVE_REWARD_OBS: collective}
       for name in self._individual:
-        value = per_player[name][i]
-        obs[name] = value if value.ndim else np.float64(value)
+        obs[name] = rgb[i] if name == 'RGB' else np.float64(host['scalar_obs'][self._scalar_index[name], 0, i])
       for name in self._global:
         obs[name] = shared[name]  # the same array object in every player's dict
       observations.append(obs)
     self._last_observation = observations
-    return dm_env.TimeStep(step_type=step_type, reward=rewards, discount=float(bts.discount[0].item()),
+    n = int(host['event_count'][0])
+    if n > host['events'].shape[1]:
+      raise RuntimeError(f'{n} events in one step exceed the engine\'s max_events {host["events"].shape[1]}')
+    self._last_events = host['events'][0, :n].numpy().copy()
+    return dm_env.TimeStep(step_type=step_type, reward=rewards, discount=float(host['discount'][0]),
                            observation=observations)
 
   # -- dm_env API -------------------------------------------------------------------------------
   def reset(self) -> dm_env.TimeStep:
-    timestep = self._to_timestep(self._batched.reset())
+    self._batched.engine.reset_host(self._host_buffers())
+    timestep = self._to_timestep()
     self._timestep_subject.on_next(timestep)
     for event in self.events():
       self._events_subject.on_next(event)
@@ -259,9 +277,10 @@ class Substrate(dm_env.Environment):
       if not 0 <= int(a) < spec.num_values:
         raise ValueError(f'action {a} out of range [0, {spec.num_values})')
     self._action_subject.on_next(action)
-    acts = self._torch.as_tensor(np.asarray(action, np.int32).reshape(1, -1),
-                                 device=self._torch.device('cuda', self._batched.engine.device))
-    timestep = self._to_timestep(self._batched.step(acts))
+    host = self._host_buffers()
+    self._host_actions[0] = self._torch.as_tensor(np.asarray(action, np.int32))
+    self._batched.engine.step_host(self._host_actions, host)
+    timestep = self._to_timestep()
     self._timestep_subject.on_next(timestep)
     for event in self.events():
       self._events_subject.on_next(event)
@@ -277,10 +296,7 @@ class Substrate(dm_env.Environment):
     order within a step is engine-defined and unpinned; here they are sorted by (type, arguments).
     """
     from meltingpot_b200 import engine as engine_lib  # pylint: disable=g-import-not-at-top
-    eng = self._batched.engine
-    self._torch.cuda.synchronize(eng.device)
-    n = min(int(eng.event_count[0].item()), int(eng.events.shape[1]))
-    rows = sorted(tuple(int(v) for v in row) for row in eng.events[0, :n].cpu().numpy())
+    rows = sorted(tuple(int(v) for v in row) for row in self._last_events)
     out = []
     for kind, a, b in rows:
       payload = [b'dict']

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_exactly_one_json_line_with_the_contract_keys():
-  out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0', '--ref-seconds', '1'],
                        capture_output=True, text=True, timeout=300, cwd=ROOT)
   assert out.returncode == 0, out.stderr[-500:]
   lines = [l for l in out.stdout.splitlines() if l.strip()]
@@ -26,7 +26,7 @@ def test_reference_arm_prints_exactly_one_json_line_with_the_contract_keys():
 
 def test_reference_arm_is_silent_on_other_ranks():
   env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
-  out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'],
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0', '--ref-seconds', '1'],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
   assert out.returncode == 0 and out.stdout.strip() == ''
 

@@ -33,3 +33,62 @@ def test_two_gpu_shards_equal_one_batch(territory_blob):
     assert np.array_equal(full.world_rgb[sl].cpu().numpy(), s.world_rgb.cpu().numpy())
     assert np.array_equal(full.reward[sl].cpu().numpy(), s.reward.cpu().numpy())
     assert np.array_equal(full.timestep_packed[sl].cpu().numpy(), s.timestep_packed.cpu().numpy())
+
+
+def test_exchange_world_of_one_gathers_own_rows(clean_up_blob):
+  # The publish path of the state-transition kernel (peer stores + flag + flow control) with the only peer being
+  # this rank itself: `gathered` must track timestep_packed on every step, on alternating slots, incl. masked resets.
+  import torch
+  from meltingpot_b200 import engine
+  B = 96
+  eng = engine.Engine(clean_up_blob, B, device=0, seed=5)
+  ptr, nbytes = eng.exchange_create(0, 1)
+  assert nbytes == 256 + 2 * B * (eng.num_players + 2) * 8
+  eng.exchange_connect([ptr])
+  gen = torch.Generator(device='cuda').manual_seed(0)
+  eng.reset()
+  slots = set()
+  for t in range(40):
+    eng.exchange_wait()
+    torch.cuda.synchronize()
+    slot, step = eng.exchange_slot()
+    assert step == t + 1
+    slots.add(slot)
+    assert torch.equal(eng.gathered_timestep(), eng.timestep_packed), t
+    if t == 20:
+      mask = torch.zeros(B, dtype=torch.uint8, device='cuda'); mask[::3] = 1
+      eng.reset(mask)   # envs outside the mask republish their unchanged rows into the new slot
+    else:
+      eng.step(torch.randint(0, 9, (B, 7), generator=gen, device='cuda', dtype=torch.int32))
+  assert slots == {0, 1}
+
+
+def test_exchange_two_gpus_one_process(territory_blob):
+  # Two ranks in ONE process (peer access enabled directly instead of CUDA IPC): after every step both ranks hold the
+  # same stacked rows, equal to the timestep of the unsharded batch.
+  import torch
+  from meltingpot_b200 import engine
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs 2 GPUs')
+  B, P = 48, 9
+  full = engine.Engine(territory_blob, 2 * B, device=0, seed=7)
+  ranks = [engine.Engine(territory_blob, B, device=r, seed=7, env_index_base=r * B) for r in range(2)]
+  ptrs = [e.exchange_create(r, 2)[0] for r, e in enumerate(ranks)]
+  engine.enable_peer_access(0, 1); engine.enable_peer_access(1, 0)
+  for e in ranks:
+    e.exchange_connect(ptrs)
+  full.reset()
+  for e in ranks:
+    e.reset()
+  gen = torch.Generator().manual_seed(1)
+  for t in range(50):
+    a = torch.randint(0, 9, (2 * B, P), generator=gen, dtype=torch.int32)
+    full.step(a.cuda(0))
+    for r, e in enumerate(ranks):
+      e.step(a[r * B:(r + 1) * B].contiguous().cuda(r))
+    for e in ranks:
+      e.exchange_wait()
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    want = full.timestep_packed.cpu()
+    for e in ranks:
+      assert torch.equal(e.gathered_timestep().cpu(), want), t
