@@ -87,6 +87,58 @@ bool make_beam_geom(int length, int radius, BeamGeom* g) {
   return true;
 }
 
+// Deals the cells of one strip to lanes so that the 64-bit staging stores of every half-warp are bank-conflict free.
+// A strip is `n_rows` pixel rows (8 for a player cell-row, 4 or 2 for WORLD.RGB) by `n_cells` cells of 24 bytes at a
+// row pitch of `pitch_slots` 8-byte slots; lane l draws pixel row l % n_rows in each of its `iters` turns. A 64-bit
+// shared store is served per half-warp and lane (row j, cell c) touches bank pair (pitch_slots * j + 3 * c) mod 16,
+// so each half-warp turn may hold every residue once and every row 16 / n_rows times: an edge colouring of the
+// bipartite multigraph rows x residues with one colour per half-warp turn (Koenig: it exists whenever no residue occurs
+// more often than there are half-warp turns). Returns false in that case (the caller keeps the plain dealing).
+bool make_lane_map(int n_rows, int n_cells, int pitch_slots, int iters, uint32_t out[32]) {
+  const int cap = 16 / n_rows, nH = 2 * iters;
+  struct Edge { int u, v, cell, col; };
+  std::vector<Edge> edges;
+  int cnt[16] = {};
+  for (int j = 0; j < n_rows; ++j)
+    for (int c = 0; c < n_cells; ++c) {
+      const int r = (pitch_slots * j + 3 * c) & 15;
+      edges.push_back({j * cap + c % cap, r, c, -1});
+      if (++cnt[r] > nH) return false;
+    }
+  if (n_cells > cap * nH || iters * 6 > 32) return false;
+  const int nL = n_rows * cap;
+  std::vector<int> colL((size_t)nL * nH, -1), colR((size_t)16 * nH, -1);  // (vertex, colour) -> edge
+  auto free_col = [&](const std::vector<int>& tab, int v) { for (int a = 0; a < nH; ++a) if (tab[(size_t)v * nH + a] < 0) return a; return -1; };
+  for (int ei = 0; ei < (int)edges.size(); ++ei) {
+    Edge& e = edges[ei];
+    const int a = free_col(colL, e.u), b = free_col(colR, e.v);
+    if (a < 0 || b < 0) return false;
+    if (a != b) {  // swap colours a / b along the alternating path that starts at e.v with colour a
+      std::vector<int> path;
+      int cur = e.v, want = a; bool right = true;
+      for (;;) {
+        const int pe = right ? colR[(size_t)cur * nH + want] : colL[(size_t)cur * nH + want];
+        if (pe < 0) break;
+        path.push_back(pe);
+        cur = right ? edges[pe].u : edges[pe].v;
+        right = !right;
+        want = want == a ? b : a;
+      }
+      for (int pe : path) { colL[(size_t)edges[pe].u * nH + edges[pe].col] = -1; colR[(size_t)edges[pe].v * nH + edges[pe].col] = -1; }
+      for (int pe : path) { edges[pe].col = edges[pe].col == a ? b : a; colL[(size_t)edges[pe].u * nH + edges[pe].col] = pe; colR[(size_t)edges[pe].v * nH + edges[pe].col] = pe; }
+    }
+    e.col = a;
+    colL[(size_t)e.u * nH + a] = ei; colR[(size_t)e.v * nH + a] = ei;
+  }
+  for (int l = 0; l < 32; ++l) { out[l] = 0; for (int i = 0; i < iters; ++i) out[l] |= 63u << (6 * i); }
+  for (const Edge& e : edges) {
+    const int j = e.u / cap, sub = e.u % cap, it = e.col / 2, half = e.col % 2;
+    const int lane = 16 * half + sub * n_rows + j;
+    out[lane] = (out[lane] & ~(63u << (6 * it))) | ((uint32_t)e.cell << (6 * it));
+  }
+  return true;
+}
+
 }  // namespace
 
 struct mp_engine {
@@ -124,6 +176,7 @@ struct mp_engine {
   int black_sprite = -1;
   std::vector<std::pair<void*, size_t>> state_spans;  // what mp_state_save / mp_state_load copy
   uint64_t state_bytes = 0;
+  int lane_map_players = 0, lane_map_world = 0;  // 1 = conflict-free dealing found (make_lane_map)
   uint64_t blob_hash = 0;  // FNV-1a of the compiled blob: a snapshot only loads into an engine built from the same blob
 
   template <typename T>
@@ -593,11 +646,16 @@ int build_plan(mp_engine* E) {
 int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int mode, cudaStream_t st) {
   const int blocks = (E->B + 3) / 4;
   if (E->S.x_world) E->S.x_step = ++E->x_seq;
-  if (E->family == MPB_FAMILY_CLEAN_UP) k_step_clean_up<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
-  else if (E->family == MPB_FAMILY_COMMONS_HARVEST) k_step_commons<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
-  else if (E->family == MPB_FAMILY_COINS) k_step_coins<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
-  else if (E->family == MPB_FAMILY_COOP_MINING) k_step_mining<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
-  else k_step_territory<<<blocks, 128, E->step_smem * 4, st>>>(E->T, E->S, actions, mask, mode);
+  void (*fn)(Tables, State, const int32_t*, const uint8_t*, int) =
+      E->family == MPB_FAMILY_CLEAN_UP ? k_step_clean_up : E->family == MPB_FAMILY_COMMONS_HARVEST ? k_step_commons :
+      E->family == MPB_FAMILY_COINS ? k_step_coins : E->family == MPB_FAMILY_COOP_MINING ? k_step_mining : k_step_territory;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = E->step_smem * 4; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, E->T, E->S, actions, mask, mode));
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;
@@ -605,7 +663,7 @@ int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int 
 
 int launch_render(mp_engine* E, cudaStream_t st) {
   if (!(E->flags & (MP_FLAG_RENDER_WORLD | MP_FLAG_RENDER_PLAYERS))) return MP_OK;
-  const int blocks = std::min((E->B + E->R.n_teams - 1) / E->R.n_teams, E->sm_count);
+  const int blocks = std::min(E->B, E->sm_count);  // every CTA has at least one env (balanced rounds + cooperative tail)
   RenderPlan R = E->R;
   const Tables& T = E->T;
   R.n_player_items = (E->flags & MP_FLAG_RENDER_PLAYERS) ? T.P * R.view_h : 0;
@@ -614,7 +672,15 @@ int launch_render(mp_engine* E, cudaStream_t st) {
   R.pitem_bytes = R.prow_bytes * 8; R.witem_bytes = R.wrow_bytes << R.wstrip_log2;
   R.h_oob = 0x8000 | (T.oob_sprite * 4); R.h_oov = 0x8000 | (T.oov_sprite * 4);
   R.h_empty = E->black_sprite >= 0 ? (0x8000 | (E->black_sprite * 4)) : 0;
-  E->render_fn<<<blocks, R.n_teams * R.team_threads, R.smem_bytes, st>>>(E->T, E->S, R, E->flags);
+  // Programmatic dependent launch: the renderer's prologue (atlas + table staging, ~3 us) runs under the tail of the
+  // state-transition kernel that precedes it in the stream; it reads env state only after griddepcontrol.wait.
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(R.n_teams * R.team_threads); cfg.dynamicSmemBytes = R.smem_bytes; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, E->render_fn, E->T, E->S, R, E->flags));
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;
@@ -729,6 +795,12 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
     else if (ncp <= 3 && ncw <= 5) E->render_fn = k_render<3, 5>;
     else if (ncp <= 4 && ncw <= 5) E->render_fn = k_render<4, 5>;
     else { mp_destroy(E); return fail(MP_E_UNSUPPORTED, "view of %d cells / map of %d cells wide (max 16 / 40)", E->R.view_w, T.W); }
+    // lane -> cell dealing: bank-conflict free where a colouring exists, else the plain one (cell = group + stride * turn)
+    const int wrows = 1 << E->R.wstrip_log2;
+    if (!(flags & MP_FLAG_DEBUG_PLAIN_LANE_MAP) && make_lane_map(8, E->R.view_w, 3 * E->R.view_w, ncp, E->R.pmap)) E->lane_map_players = 1;
+    else for (int l = 0; l < 32; ++l) { E->R.pmap[l] = 0; for (int i = 0; i < 4; ++i) E->R.pmap[l] |= (uint32_t)std::min(63, (l >> 3) + 4 * i) << (6 * i); }
+    if (!(flags & MP_FLAG_DEBUG_PLAIN_LANE_MAP) && make_lane_map(wrows, T.W, 3 * T.W, ncw, E->R.wmap)) E->lane_map_world = 1;
+    else for (int l = 0; l < 32; ++l) { E->R.wmap[l] = 0; for (int i = 0; i < 5; ++i) E->R.wmap[l] |= (uint32_t)std::min(63, (l >> E->R.wstrip_log2) + (32 >> E->R.wstrip_log2) * i) << (6 * i); }
   }
   // The attribute belongs to the kernel function, not to this handle: engines that share an instantiation must not
   // lower each other's limit, so the renderer always gets the opt-in maximum and the step kernels only ever raise theirs.
@@ -1064,6 +1136,12 @@ int mp_debug_render_tables(mp_handle h, int32_t* n_total, uint8_t* pair, uint8_t
   if (n_total) *n_total = h->n_total;
   if (pair) memcpy(pair, h->host_pair.data(), h->host_pair.size());
   if (flags) memcpy(flags, h->host_sflags.data(), h->host_sflags.size());
+  return MP_OK;
+}
+
+int mp_debug_lane_map(int n_rows, int n_cells, int pitch_slots, int iters, uint32_t out[32]) {
+  if (!out || (n_rows != 8 && n_rows != 4 && n_rows != 2) || n_cells < 1 || n_cells > 62 || iters < 1 || iters > 5) return fail(MP_E_INVALID, "mp_debug_lane_map: bad arguments");
+  if (!make_lane_map(n_rows, n_cells, pitch_slots, iters, out)) return fail(MP_E_UNSUPPORTED, "no conflict-free dealing for %d rows x %d cells in %d turns", n_rows, n_cells, iters);
   return MP_OK;
 }
 

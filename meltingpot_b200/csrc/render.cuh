@@ -62,6 +62,10 @@ struct RenderPlan {  // host-computed constants of the tiling
   int pitem_bytes, witem_bytes;          // one strip
   int h_oob, h_oov;                      // fast-path headers of the OutOfBounds / OutOfView sprites
   int h_empty;                           // header of a cell with nothing visible: fast path to an opaque black sprite, or 0
+  // Which cell each lane draws in each of its NCP / NCW turns on a strip (6 bits per turn, 63 = none). The lane's
+  // pixel row stays lane & 7 (player strips) / lane & (rows - 1) (WORLD.RGB strips); the cells are dealt so that the
+  // 16 lanes of every half-warp hit 16 different bank pairs with their 64-bit staging stores (host: make_lane_map).
+  uint32_t pmap[32], wmap[32];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,7 +111,7 @@ __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void team_sync(int team, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(threads) : "memory"); }
+__device__ __forceinline__ void group_sync(int bar_id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(threads) : "memory"); }
 
 // dst, src: R | G<<8 | B<<16 (| A<<24 for src). Integer "over": (s*a + d*(255-a)) / 255, truncated.
 // Branch free on purpose: a == 255 yields src and a == 0 yields dst exactly, so opaque sprites and
@@ -168,8 +172,8 @@ __device__ __forceinline__ void compose_row(uint32_t px[8], const uint8_t* __res
 // unrolled; the layers that matter are then found with bit masks (most cells hold one sprite).
 template <int LMAX>
 __device__ __forceinline__ void cell_pass(const Tables& T, const RenderPlan& R, const uint16_t* __restrict__ s_grid, uint16_t* __restrict__ s_rec,
-                                          const uint8_t* __restrict__ s_flags, const uint8_t* __restrict__ s_pair, int ttid, uint32_t dbg) {
-  for (int c = ttid; c < T.cells; c += R.team_threads) {
+                                          const uint8_t* __restrict__ s_flags, const uint8_t* __restrict__ s_pair, int gtid, int gthreads, uint32_t dbg) {
+  for (int c = gtid; c < T.cells; c += gthreads) {
     uint32_t v[LMAX];
 #pragma unroll
     for (int l = 0; l < LMAX; ++l) v[l] = l < T.L ? s_grid[l * T.cells_pad + c] : 0u;
@@ -254,70 +258,99 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
   const int ttid = tid - team * R.team_threads;
   const int lane = tid & 31, twarp = ttid >> 5;
   uint8_t* s_team = smem + R.off_team0 + team * R.team_stride;
-  uint16_t* s_grid = reinterpret_cast<uint16_t*>(s_team + R.toff_grid);
+  uint16_t* s_grid = reinterpret_cast<uint16_t*>(s_team + R.toff_grid);  // (these four switch to team 0's in the cooperative tail)
   uint16_t* s_rec = reinterpret_cast<uint16_t*>(s_team + R.toff_rec);
   uint8_t* s_stage = s_team + R.toff_stage + twarp * R.stage_bytes;  // warp-private
   ViewerInfo* s_view = s_view_all[team];
   uint64_t* gbar = &bar[1 + team];
 
+  // Work split. Balanced part: `rounds` = B / (teams in the grid) envs per team, rendered team by team with no
+  // interaction between teams. Tail: the remaining B mod (teams in the grid) envs are dealt to the CTAs and each is
+  // rendered by ALL teams of its CTA together (one cell pass into team 0's records, every warp pulling that env's
+  // strips), so the kernel ends after rounds + ~1/n_teams env-times instead of rounds + 1.
   const int n_streams = gridDim.x * R.n_teams;
+  const int rounds = S.B / n_streams;
+  const int tail0 = rounds * n_streams;
+  const int n_tail = (S.B - tail0 - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // >= 0: tail envs of this CTA
+  const int n_iters = rounds + (n_tail > 0 ? n_tail : 0);
   const int first = blockIdx.x * R.n_teams + team;
   if (tid == 0) {
     for (int i = 0; i < 1 + R.n_teams; ++i) mbar_init(&bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (ttid == 0) s_next_item[team] = 0;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next state-transition kernel may queue up behind this grid
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(&bar[0], (uint32_t)R.atlas_bytes);
     bulk_load(s_atlas, T.atlas, (uint32_t)R.atlas_bytes, &bar[0]);
   }
-  if (ttid == 0 && first < S.B) {
-    mbar_expect_tx(gbar, (uint32_t)R.grid_bytes);
-    bulk_load(s_grid, S.grid + (size_t)first * T.L * T.cells_pad, (uint32_t)R.grid_bytes, gbar);
-  }
   for (int i = tid; i < (T.P + 1) * R.n_total; i += (int)blockDim.x) s_map[i] = T.sprite_map[i];
   for (int i = tid; i < R.n_total; i += (int)blockDim.x) s_opaque[i] = T.sprite_opaque[i];
   for (int i = tid; i < R.n_total * R.n_total; i += (int)blockDim.x) smem[R.off_pair + i] = T.sprite_pair[i];
+  // Everything above reads only static tables: with a programmatic dependent launch it overlaps the tail of the
+  // state-transition kernel. The env state (grid, avatars) may be read only after this point.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (ttid == 0 && rounds > 0) {
+    mbar_expect_tx(gbar, (uint32_t)R.grid_bytes);
+    bulk_load(s_grid, S.grid + (size_t)first * T.L * T.cells_pad, (uint32_t)R.grid_bytes, gbar);
+  }
   __syncthreads();  // tables visible to every warp before the first cell pass
   mbar_wait(&bar[0], 0);
-  if (first >= S.B) return;
 
   const int wlog = R.wstrip_log2, wrows = 1 << wlog;  // pixel rows per WORLD.RGB strip (2 or 4)
   const int slot_bytes = R.stage_bytes / RENDER_SLOTS;
   const uint64_t store_policy = make_evict_first_policy();
+  const uint32_t pcells = R.pmap[lane], wcells = R.wmap[lane];
   uint32_t slot = 0;
-  int it = 0;
-  for (int b = first; b < S.B; b += n_streams, ++it) {
-    if (ttid < T.P) {
-      const int4 a = *reinterpret_cast<const int4*>(S.avatar + ((size_t)b * T.P + ttid) * 4);
+  // the group that renders the current env: a team (balanced part) or the whole CTA (tail)
+  int gtid = ttid, gthreads = R.team_threads, bar_id = 1 + team;
+  int* next_ctr = &s_next_item[team];
+  for (int it = 0; it < n_iters; ++it) {
+    if (it == rounds) {  // switch to the cooperative tail: every team is done with its own envs
+      __syncthreads();
+      uint8_t* s_team0 = smem + R.off_team0;
+      s_grid = reinterpret_cast<uint16_t*>(s_team0 + R.toff_grid);
+      s_rec = reinterpret_cast<uint16_t*>(s_team0 + R.toff_rec);
+      s_view = s_view_all[0];
+      gbar = &bar[1];
+      next_ctr = &s_next_item[0];
+      gtid = tid; gthreads = (int)blockDim.x; bar_id = 0;
+      if (tid == 0) {
+        mbar_expect_tx(gbar, (uint32_t)R.grid_bytes);
+        bulk_load(s_grid, S.grid + (size_t)(tail0 + (int)blockIdx.x) * T.L * T.cells_pad, (uint32_t)R.grid_bytes, gbar);
+      }
+    }
+    const int b = it < rounds ? first + it * n_streams : tail0 + (int)blockIdx.x + (it - rounds) * (int)gridDim.x;
+    if (gtid < T.P) {
+      const int4 a = *reinterpret_cast<const int4*>(S.avatar + ((size_t)b * T.P + gtid) * 4);
       ViewerInfo vi;
       vi.ax = a.x; vi.ay = a.y; vi.ao = a.z; vi.alive = a.w;
       vi.fdx = dir_dx(a.z); vi.fdy = dir_dy(a.z); vi.rdx = dir_dx((a.z + 1) & 3); vi.rdy = dir_dy((a.z + 1) & 3);
-      s_view[ttid] = vi;
+      s_view[gtid] = vi;
     }
-    mbar_wait(gbar, (uint32_t)(it & 1));
+    mbar_wait(gbar, (uint32_t)(it & 1));  // (team 0's barrier has completed `rounds` phases when the tail starts, so the parity carries over)
     // ---- per-cell pass: flatten the layer stack, folding map sprites into pre-merged ones -------
     if (!(flags & 64u) || it == 0) {  // (bit 6: debug -- reuse the first env's records)
-      if (T.L <= 8) cell_pass<8>(T, R, s_grid, s_rec, s_opaque, s_pair, ttid, flags);
-      else if (T.L <= 10) cell_pass<10>(T, R, s_grid, s_rec, s_opaque, s_pair, ttid, flags);
-      else if (T.L <= 12) cell_pass<12>(T, R, s_grid, s_rec, s_opaque, s_pair, ttid, flags);
-      else cell_pass<MP_MAX_LAYERS>(T, R, s_grid, s_rec, s_opaque, s_pair, ttid, flags);
+      if (T.L <= 8) cell_pass<8>(T, R, s_grid, s_rec, s_opaque, s_pair, gtid, gthreads, flags);
+      else if (T.L <= 10) cell_pass<10>(T, R, s_grid, s_rec, s_opaque, s_pair, gtid, gthreads, flags);
+      else if (T.L <= 12) cell_pass<12>(T, R, s_grid, s_rec, s_opaque, s_pair, gtid, gthreads, flags);
+      else cell_pass<MP_MAX_LAYERS>(T, R, s_grid, s_rec, s_opaque, s_pair, gtid, gthreads, flags);
     }
-    team_sync(team, R.team_threads);  // records complete; the grid buffer is free again
-    const int nb = b + n_streams;
-    if (ttid == 0 && nb < S.B) {
+    group_sync(bar_id, gthreads);  // records complete; the grid buffer is free again
+    if (gtid == 0 && it + 1 < n_iters && it + 1 != rounds) {  // (the first tail env is fetched at the switch)
+      const int nb = it + 1 < rounds ? b + n_streams : b + (int)gridDim.x;
       mbar_expect_tx(gbar, (uint32_t)R.grid_bytes);
       bulk_load(s_grid, S.grid + (size_t)nb * T.L * T.cells_pad, (uint32_t)R.grid_bytes, gbar);
     }
 
     // ---- strip items, pulled by warps -------------------------------------------------------------
     int next_item = 0;  // claimed one strip ahead so that the atomic's latency hides behind the strip being drawn
-    if (lane == 0) next_item = atomicAdd(&s_next_item[team], 1);
+    if (lane == 0) next_item = atomicAdd(next_ctr, 1);
     for (;;) {
       const int item = __shfl_sync(MP_FULL, next_item, 0);
       if (item >= R.n_items) break;
-      if (lane == 0) next_item = atomicAdd(&s_next_item[team], 1);
+      if (lane == 0) next_item = atomicAdd(next_ctr, 1);
       uint8_t* buf = s_stage + (slot % RENDER_SLOTS) * slot_bytes;
       ++slot;
       if (lane == 0) bulk_wait_read<RENDER_SLOTS - 1>();  // the store that last used this slot has drained
@@ -326,13 +359,13 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
         const int p = (int)(((uint32_t)item * R.magic_view_h) >> 16), cy = item - p * R.view_h;
         const ViewerInfo vi = s_view[p];
         const int16_t* map = s_map + p * R.n_total;
-        const int py = lane & 7, cg = lane >> 3;
+        const int py = lane & 7;
         const int df = T.view_f - cy;
         const int bx = vi.ax + vi.fdx * df - vi.rdx * T.view_l, by = vi.ay + vi.fdy * df - vi.rdy * T.view_l;
         int hdr[NCP];
         if (!(flags & 16u)) {  // (bit 4: debug / ceiling measurement -- issue the stores without composing)
         // lane cx resolves view cell cx once: a single-sprite cell becomes REC_FAST | sprite * 4 + facing as this
-        // viewer sees it, anything else the cell index; the 8 lanes that draw the cell's rows fetch it by shuffle
+        // viewer sees it, anything else the cell index; the lanes that draw the cell's rows fetch it by shuffle
         int myh = R.h_oov;
         if (lane < R.view_w && vi.alive) {
           int wx = bx + vi.rdx * lane, wy = by + vi.rdy * lane;
@@ -344,10 +377,10 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
           }
         }
 #pragma unroll
-        for (int i = 0; i < NCP; ++i) hdr[i] = __shfl_sync(MP_FULL, myh, cg + 4 * i);
+        for (int i = 0; i < NCP; ++i) hdr[i] = __shfl_sync(MP_FULL, myh, (pcells >> (6 * i)) & 31);
 #pragma unroll
         for (int i = 0; i < NCP; ++i) {  // ... then each cell's sprite row: load (a multi-sprite cell loads a dummy), composite, pack, stage
-          const int cx = cg + 4 * i;
+          const int cx = (pcells >> (6 * i)) & 63;
           uint32_t q[8];
           fast_row(q, s_atlas, (hdr[i] & REC_FAST) ? hdr[i] : 0, py);
           if (!(hdr[i] & REC_FAST)) compose_row(q, s_atlas, s_rec + hdr[i] * R.rec_stride, map, vi.ao, py);
@@ -359,20 +392,19 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
         if (lane == 0 && !(flags & 32u)) bulk_store(S.rgb + ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * R.pitem_bytes, buf, (uint32_t)R.pitem_bytes, store_policy);
       } else {
         const int wi = item - R.n_player_items, wy = wi >> (3 - wlog);
-        const int py = ((wi & ((8 >> wlog) - 1)) << wlog) | (lane & (wrows - 1)), cg = lane >> wlog;
-        const int cstep = 32 >> wlog;
+        const int py = ((wi & ((8 >> wlog) - 1)) << wlog) | (lane & (wrows - 1));
         const int16_t* map = s_map + T.P * R.n_total;
         const uint16_t* rowrec = s_rec + wy * T.W * R.rec_stride;
         int hdr[NCW];
         if (!(flags & 16u)) {
 #pragma unroll
         for (int i = 0; i < NCW; ++i) {
-          const int cx = cg + cstep * i;
+          const int cx = (wcells >> (6 * i)) & 63;
           hdr[i] = cx < T.W ? (int)rowrec[cx * R.rec_stride] : R.h_oov;
         }
 #pragma unroll
         for (int i = 0; i < NCW; ++i) {
-          const int cx = cg + cstep * i;
+          const int cx = (wcells >> (6 * i)) & 63;
           uint32_t q[8];
           fast_row(q, s_atlas, (hdr[i] & REC_FAST) ? hdr[i] : 0, py);
           if (!(hdr[i] & REC_FAST)) compose_row(q, s_atlas, rowrec + min(cx, T.W - 1) * R.rec_stride, map, 0, py);
@@ -384,9 +416,9 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
         if (lane == 0 && !(flags & 32u)) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wi * R.witem_bytes, buf, (uint32_t)R.witem_bytes, store_policy);
       }
     }
-    team_sync(team, R.team_threads);  // every warp is done with s_rec / s_view
-    if (ttid == 0) s_next_item[team] = 0;
-    // (the reset is ordered before the next env's item loop by the team barrier after its cell pass)
+    group_sync(bar_id, gthreads);  // every warp is done with s_rec / s_view
+    if (gtid == 0) *next_ctr = 0;
+    // (the reset is ordered before the next env's item loop by the group barrier after its cell pass)
   }
   if (lane == 0) bulk_wait_read<0>();
 }

@@ -422,6 +422,10 @@ __global__ void __launch_bounds__(128) k_step_territory(Tables T, State S, const
                                                        const uint8_t* __restrict__ mask, int mode) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Programmatic dependent launch, both ways: let the renderer that follows in the stream stage its tables while this
+  // grid drains, and do not touch env state before the kernel that precedes this one (the previous render) is complete.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int b = blockIdx.x * 4 + warp;
   if (b >= S.B) return;
   TerritoryScratch sc = carve_territory(T, smem + warp * territory_scratch_bytes(T));

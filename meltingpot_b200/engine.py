@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     'mp_step_state', 'mp_render', 'mp_get_buffers', 'mp_step_host',
     'mp_reset_host', 'mp_launch_count', 'mp_algorithmic_bytes', 'mp_debug_render_tables', 'mp_debug_render_plan', 'mp_state_size', 'mp_state_save', 'mp_state_load',
     'mp_step_host_async', 'mp_wait', 'mp_exchange_create', 'mp_ipc_export', 'mp_ipc_open', 'mp_enable_peer_access',
-    'mp_exchange_connect', 'mp_exchange_wait', 'mp_exchange_slot',
+    'mp_exchange_connect', 'mp_exchange_wait', 'mp_exchange_slot', 'mp_debug_lane_map',
     'mp_last_error', 'mp_version',
 )
 
@@ -101,6 +101,7 @@ def load_library() -> ctypes.CDLL:
   lib.mp_exchange_connect.argtypes = [vp, ctypes.POINTER(vp)]
   lib.mp_exchange_wait.argtypes = [vp, vp]
   lib.mp_exchange_slot.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint64)]
+  lib.mp_debug_lane_map.argtypes = [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_uint32)]
   lib.mp_last_error.restype = ctypes.c_char_p
   lib.mp_version.restype = ctypes.c_char_p
   _lib = lib

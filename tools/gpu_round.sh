@@ -1,11 +1,16 @@
 #!/bin/bash
-# One GPU-box visit: parity suite, bench, launch list, full ncu captures of the two kernels.
-set -x
+# One GPU-box visit: GPU tests, the bench line of the headline config, A/B of the lane dealing, ncu captures.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 1500 gpurun_out/bench.json
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; tail -c 600 gpurun_out/bench_ref.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 40 --warmup 3 --e2e-steps 2 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_render -s 5 -c 1 -o gpurun_out/render python bench.py --steps 10 --warmup 3 --e2e-steps 1 --no-cpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_step -s 5 -c 1 -o gpurun_out/step python bench.py --steps 10 --warmup 3 --e2e-steps 1 --no-cpu-baseline > /dev/null 2>&1
-python tools/throughput_all.py > gpurun_out/throughput.jsonl 2>> gpurun_out/bench.err; cat gpurun_out/throughput.jsonl | cut -c1-300
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python tools/ab_lane_map.py 2>&1 | tail -5 | tee gpurun_out/ab_lane_map.jsonl
+python bench.py --config 2 --steps 1000 --warmup 20 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err || tail -5 gpurun_out/bench_c2.err
+python - <<PY
+import json
+l=json.load(open('gpurun_out/bench_c2.json'))
+print('config 2', round(l['value']), 'ms', round(l['ms_per_step'],4), 'render', l['roofline']['ms_per_launch'], 'frac', round(l['roofline']['frac'],3), 'whole', l['roofline']['whole_step_frac'], 'e2e', l.get('e2e',{}).get('value'))
+PY
+ncu --set full --clock-control none --import-source on -k regex:k_render -s 4 -c 1 -f -o gpurun_out/render_r02 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 4 > gpurun_out/ncu_render.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_step -s 4 -c 1 -f -o gpurun_out/step_r02 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --e2e-steps 4 > gpurun_out/ncu_step.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 4 > gpurun_out/ncu_launches.log 2>&1
+ls -la gpurun_out | tail -8
