@@ -44,7 +44,8 @@ enum {
   MP_FLAG_DEBUG_REUSE_RECORDS = 1u << 6, /* per-cell pass only for the first env of each team */
   MP_FLAG_DEBUG_NO_FENCE = 1u << 7,     /* skip the generic->async proxy fence */
   MP_FLAG_DEBUG_TOP_SPRITE_ONLY = 1u << 8, /* every cell drawn as its top sprite */
-  MP_FLAG_DEBUG_PLAIN_LANE_MAP = 1u << 9   /* mp_create only: deal cells to lanes without the bank-conflict-free colouring (A/B) */
+  MP_FLAG_DEBUG_PLAIN_LANE_MAP = 1u << 9,  /* mp_create only: deal cells to lanes in plain order (A/B) */
+  MP_FLAG_DEBUG_SCATTER_LANE_MAP = 1u << 10 /* mp_create only: fully conflict-free dealing that scatters a cell's rows over turns (A/B) */
 };
 
 /* Device buffers owned by the engine; valid until mp_destroy. Contents are overwritten by the
@@ -200,8 +201,9 @@ int mp_debug_render_tables(mp_handle h, int32_t* n_total, uint8_t* pair, uint8_t
 
 /* Diagnostic (needs no device): the renderer's lane -> cell dealing for a strip of `n_rows` pixel rows x `n_cells` cells
  * at a row pitch of `pitch_slots` 8-byte slots, `iters` turns per lane: out[lane] holds 6 bits per turn (63 = idle).
- * Lane l draws pixel row l % n_rows; the dealing makes the 64-bit staging stores of every half-warp bank-conflict free. */
-int mp_debug_lane_map(int n_rows, int n_cells, int pitch_slots, int iters, uint32_t out[32]);
+ * Lane l draws pixel row l % n_rows. scattered = 0: the default dealing (whole cells per lane group and turn, cell order
+ * chosen to minimise bank conflicts of the 64-bit staging stores); 1: the fully conflict-free colouring (A/B flag). */
+int mp_debug_lane_map(int n_rows, int n_cells, int pitch_slots, int iters, int scattered, uint32_t out[32]);
 
 const char* mp_last_error(void);
 const char* mp_version(void);

@@ -150,14 +150,27 @@ enum { EV_ZAP = 1, EV_EDIBLE_CONSUMED = 2, EV_PLAYER_CLEANED = 3, EV_CLAIMED_RES
        EV_MINING = 9 /* a = player, b = ore type */, EV_EXTRACTION = 10 /* a = player, b = ore type */,
        EV_EXTRACTION_PAIR = 11 /* a = player_a, b = player_b | ore type << 8 */ };
 
-// Called by the one lane that owns the event. Lanes append concurrently, so the order within a
-// step is unspecified (hosts sort); the per-env counter is zeroed at kernel entry.
+// Called by the one lane that owns the event. Lanes append concurrently, so the order within a step is unspecified
+// (hosts sort). One warp owns an env, so the step's event count lives in shared memory (a global atomic per event
+// would put its round trip on the warp's critical path); event_end publishes it once.
+__device__ __forceinline__ int* event_counter() {
+  __shared__ int s_event_count[4];  // one per env warp of a state-transition CTA
+  return &s_event_count[(threadIdx.x >> 5) & 3];
+}
+__device__ __forceinline__ void event_begin(int lane) {
+  if (lane == 0) *event_counter() = 0;
+  __syncwarp();
+}
 __device__ __forceinline__ void emit_event(const State& S, int b, int type, int a0, int a1) {
-  const int i = atomicAdd(&S.n_events[b], 1);
+  const int i = atomicAdd(event_counter(), 1);
   if (i < S.max_events) {  // (always true: max_events bounds what one step can emit; kept as a memory-safety guard)
     int32_t* e = S.events + ((size_t)b * S.max_events + i) * 3;
     e[0] = type; e[1] = a0; e[2] = a1;
   }
+}
+__device__ __forceinline__ void event_end(const State& S, int b, int lane) {
+  __syncwarp();
+  if (lane == 0) S.n_events[b] = *event_counter();
 }
 
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {

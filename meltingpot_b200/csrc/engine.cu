@@ -139,6 +139,53 @@ bool make_lane_map(int n_rows, int n_cells, int pitch_slots, int iters, uint32_t
   return true;
 }
 
+// The dealing used by default: every cell keeps all its pixel rows on `n_rows` consecutive lanes and in ONE turn (so a
+// multi-sprite cell sends a warp through the slow compositing path once, not once per turn it was scattered over), and
+// only WHICH cell sits on which lane group in which turn is chosen, to minimise the extra wavefronts of the staging
+// stores: sum over half-warp turns of (largest number of lanes on one bank pair - 1). Steepest-descent over pair swaps
+// from the plain dealing; deterministic. Returns the remaining extra wavefronts per strip.
+int make_lane_map_cells(int n_rows, int n_cells, int pitch_slots, int iters, uint32_t out[32]) {
+  const int G = 32 / n_rows, n_slots = G * iters, per_half = 16 / n_rows;
+  std::vector<int> slot(n_slots, -1);
+  for (int c = 0; c < n_cells && c < n_slots; ++c) slot[c] = c;  // plain: slot index = turn * G + group
+  auto cost = [&]() {
+    int total = 0;
+    for (int it = 0; it < iters; ++it)
+      for (int h = 0; h < 2; ++h) {
+        int cnt[16] = {}, mx = 0;
+        for (int g = h * per_half; g < (h + 1) * per_half; ++g) {
+          const int c = slot[it * G + g];
+          if (c < 0) continue;
+          for (int j = 0; j < n_rows; ++j) mx = std::max(mx, ++cnt[(pitch_slots * j + 3 * c) & 15]);
+        }
+        total += mx > 1 ? mx - 1 : 0;
+      }
+    return total;
+  };
+  int best = cost();
+  for (bool improved = true; improved && best > 0;) {
+    improved = false;
+    int bi = -1, bj = -1, bc = best;
+    for (int i = 0; i < n_slots; ++i)
+      for (int j = i + 1; j < n_slots; ++j) {
+        if (slot[i] == slot[j]) continue;
+        std::swap(slot[i], slot[j]);
+        const int c = cost();
+        if (c < bc) { bc = c; bi = i; bj = j; }
+        std::swap(slot[i], slot[j]);
+      }
+    if (bi >= 0) { std::swap(slot[bi], slot[bj]); best = bc; improved = true; }
+  }
+  for (int l = 0; l < 32; ++l) {
+    out[l] = 0;
+    for (int it = 0; it < 5; ++it) {
+      const int c = it < iters ? slot[it * G + l / n_rows] : -1;
+      out[l] |= (uint32_t)(c < 0 ? 63 : c) << (6 * it);
+    }
+  }
+  return best;
+}
+
 }  // namespace
 
 struct mp_engine {
@@ -176,7 +223,7 @@ struct mp_engine {
   int black_sprite = -1;
   std::vector<std::pair<void*, size_t>> state_spans;  // what mp_state_save / mp_state_load copy
   uint64_t state_bytes = 0;
-  int lane_map_players = 0, lane_map_world = 0;  // 1 = conflict-free dealing found (make_lane_map)
+  int lane_map_players = 0, lane_map_world = 0;  // 0 plain, 2 scattered colouring, 1 + 16 * (extra wavefronts left) whole-cell dealing
   uint64_t blob_hash = 0;  // FNV-1a of the compiled blob: a snapshot only loads into an engine built from the same blob
 
   template <typename T>
@@ -795,12 +842,19 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
     else if (ncp <= 3 && ncw <= 5) E->render_fn = k_render<3, 5>;
     else if (ncp <= 4 && ncw <= 5) E->render_fn = k_render<4, 5>;
     else { mp_destroy(E); return fail(MP_E_UNSUPPORTED, "view of %d cells / map of %d cells wide (max 16 / 40)", E->R.view_w, T.W); }
-    // lane -> cell dealing: bank-conflict free where a colouring exists, else the plain one (cell = group + stride * turn)
+    // lane -> cell dealing (see make_lane_map_cells / make_lane_map): whole cells per lane group with the cell order chosen
+    // to minimise store bank conflicts by default; the fully conflict-free scattered colouring or the plain order for A/B.
     const int wrows = 1 << E->R.wstrip_log2;
-    if (!(flags & MP_FLAG_DEBUG_PLAIN_LANE_MAP) && make_lane_map(8, E->R.view_w, 3 * E->R.view_w, ncp, E->R.pmap)) E->lane_map_players = 1;
-    else for (int l = 0; l < 32; ++l) { E->R.pmap[l] = 0; for (int i = 0; i < 4; ++i) E->R.pmap[l] |= (uint32_t)std::min(63, (l >> 3) + 4 * i) << (6 * i); }
-    if (!(flags & MP_FLAG_DEBUG_PLAIN_LANE_MAP) && make_lane_map(wrows, T.W, 3 * T.W, ncw, E->R.wmap)) E->lane_map_world = 1;
-    else for (int l = 0; l < 32; ++l) { E->R.wmap[l] = 0; for (int i = 0; i < 5; ++i) E->R.wmap[l] |= (uint32_t)std::min(63, (l >> E->R.wstrip_log2) + (32 >> E->R.wstrip_log2) * i) << (6 * i); }
+    if (flags & MP_FLAG_DEBUG_PLAIN_LANE_MAP) {
+      for (int l = 0; l < 32; ++l) { E->R.pmap[l] = 0; for (int i = 0; i < 4; ++i) E->R.pmap[l] |= (uint32_t)std::min(63, (l >> 3) + 4 * i) << (6 * i); }
+      for (int l = 0; l < 32; ++l) { E->R.wmap[l] = 0; for (int i = 0; i < 5; ++i) E->R.wmap[l] |= (uint32_t)std::min(63, (l >> E->R.wstrip_log2) + (32 >> E->R.wstrip_log2) * i) << (6 * i); }
+    } else if ((flags & MP_FLAG_DEBUG_SCATTER_LANE_MAP) && make_lane_map(8, E->R.view_w, 3 * E->R.view_w, ncp, E->R.pmap) &&
+               make_lane_map(wrows, T.W, 3 * T.W, ncw, E->R.wmap)) {
+      E->lane_map_players = E->lane_map_world = 2;
+    } else {
+      E->lane_map_players = 1 + 16 * make_lane_map_cells(8, E->R.view_w, 3 * E->R.view_w, ncp, E->R.pmap);
+      E->lane_map_world = 1 + 16 * make_lane_map_cells(wrows, T.W, 3 * T.W, ncw, E->R.wmap);
+    }
   }
   // The attribute belongs to the kernel function, not to this handle: engines that share an instantiation must not
   // lower each other's limit, so the renderer always gets the opt-in maximum and the step kernels only ever raise theirs.
@@ -1139,8 +1193,9 @@ int mp_debug_render_tables(mp_handle h, int32_t* n_total, uint8_t* pair, uint8_t
   return MP_OK;
 }
 
-int mp_debug_lane_map(int n_rows, int n_cells, int pitch_slots, int iters, uint32_t out[32]) {
+int mp_debug_lane_map(int n_rows, int n_cells, int pitch_slots, int iters, int scattered, uint32_t out[32]) {
   if (!out || (n_rows != 8 && n_rows != 4 && n_rows != 2) || n_cells < 1 || n_cells > 62 || iters < 1 || iters > 5) return fail(MP_E_INVALID, "mp_debug_lane_map: bad arguments");
+  if (!scattered) { if (n_cells > (32 / n_rows) * iters) return fail(MP_E_INVALID, "mp_debug_lane_map: too few turns"); make_lane_map_cells(n_rows, n_cells, pitch_slots, iters, out); return MP_OK; }
   if (!make_lane_map(n_rows, n_cells, pitch_slots, iters, out)) return fail(MP_E_UNSUPPORTED, "no conflict-free dealing for %d rows x %d cells in %d turns", n_rows, n_cells, iters);
   return MP_OK;
 }

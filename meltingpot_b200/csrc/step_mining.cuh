@@ -280,7 +280,7 @@ __device__ void mining_step(const Tables& T, const State& S, int b, int lane, co
   }
 }
 
-__global__ void __launch_bounds__(128) k_step_mining(Tables T, State S, const int32_t* __restrict__ actions,
+__global__ void __launch_bounds__(128, 8) k_step_mining(Tables T, State S, const int32_t* __restrict__ actions,
                                                     const uint8_t* __restrict__ mask, int mode) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -292,10 +292,10 @@ __global__ void __launch_bounds__(128) k_step_mining(Tables T, State S, const in
   if (b >= S.B) return;
   WarpScratch sc = carve_scratch(T, smem + warp * warp_scratch_bytes(T));
   if (!(mode == 1 && !(mask == nullptr || mask[b]))) {
-    if (lane == 0) S.n_events[b] = 0;
-    __syncwarp();
+    event_begin(lane);
     if (mode == 1 || S.env[(size_t)b * ENV_COLS + ENV_DONE]) mining_reset(T, S, b, lane, sc);
     else mining_step(T, S, b, lane, actions, sc);
+    event_end(S, b, lane);
   }
   exchange_publish(T, S, b, lane);
 }

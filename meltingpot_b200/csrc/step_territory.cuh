@@ -418,7 +418,7 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
   }
 }
 
-__global__ void __launch_bounds__(128) k_step_territory(Tables T, State S, const int32_t* __restrict__ actions,
+__global__ void __launch_bounds__(128, 8) k_step_territory(Tables T, State S, const int32_t* __restrict__ actions,
                                                        const uint8_t* __restrict__ mask, int mode) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -434,8 +434,7 @@ __global__ void __launch_bounds__(128) k_step_territory(Tables T, State S, const
   const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
   const bool reset = mode == 1 ? (mask == nullptr || mask[b]) : (env[ENV_DONE] != 0);
   if (!(mode == 1 && !reset)) {
-    if (lane == 0) S.n_events[b] = 0;
-    __syncwarp();
+    event_begin(lane);
     if (reset) {
       const int episode = env[ENV_EPISODE] + 1;
       __syncwarp();
@@ -446,6 +445,7 @@ __global__ void __launch_bounds__(128) k_step_territory(Tables T, State S, const
     } else {
       territory_frame(T, S, b, lane, actions, sc, env[ENV_STEP] + 1, env[ENV_EPISODE], k0, k1);
     }
+    event_end(S, b, lane);
   }
   exchange_publish(T, S, b, lane);
 }

@@ -101,7 +101,7 @@ def load_library() -> ctypes.CDLL:
   lib.mp_exchange_connect.argtypes = [vp, ctypes.POINTER(vp)]
   lib.mp_exchange_wait.argtypes = [vp, vp]
   lib.mp_exchange_slot.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint64)]
-  lib.mp_debug_lane_map.argtypes = [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_uint32)]
+  lib.mp_debug_lane_map.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_uint32)]
   lib.mp_last_error.restype = ctypes.c_char_p
   lib.mp_version.restype = ctypes.c_char_p
   _lib = lib

@@ -1,4 +1,5 @@
-"""A/B of the renderer's lane -> cell dealing: conflict-free colouring vs the plain one (MP_FLAG_DEBUG_PLAIN_LANE_MAP)."""
+"""A/B of the renderer's lane -> cell dealing (default whole-cell order / scattered colouring / plain) and the two ceilings
+(stores without compositing, compositing without stores)."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,7 +9,7 @@ CONFIGS = [('clean_up', 7, 4096), ('commons_harvest__open', 16, 8192), ('territo
 for name, players, B in CONFIGS:
   blob = substrates.load_blob(name, ('default',) * players)
   row = {'substrate': name, 'envs': B}
-  for label, extra in (('coloured', 0), ('plain', 1 << 9)):
+  for label, extra in (('cells', 0), ('scatter', 1 << 10), ('plain', 1 << 9), ('stores_only', 16), ('compose_only', 32)):
     eng = engine.Engine(blob, B, seed=1, flags=3 | extra)
     gen = torch.Generator(device='cuda').manual_seed(0)
     K, W = 200, 20

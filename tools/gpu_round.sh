@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python tools/ab_lane_map.py 2>&1 | tail -5 | tee gpurun_out/ab_lane_map.jsonl
+python tools/ab_lane_map.py 2>&1 | tail -5 | cut -c1-900 | tee gpurun_out/ab_lane_map.jsonl
 python bench.py --config 2 --steps 1000 --warmup 20 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err || tail -5 gpurun_out/bench_c2.err
 python - <<PY
 import json
