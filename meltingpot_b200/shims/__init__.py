@@ -1,4 +1,4 @@
-"""Dependency shims: `dm_env`, `ml_collections`, `immutabledict`.
+"""Dependency shims: `dm_env`, `ml_collections`, `immutabledict`, `tree`, `chex`, `reactivex`, `dmlab2d`.
 
 `install()` registers a stand-in module in `sys.modules` for each of these
 third-party packages that cannot be imported. The real package always wins.
@@ -37,3 +37,16 @@ def install() -> None:
       sys.modules['ml_collections.config_dict'] = config_dict
     if need_imm:
       sys.modules['immutabledict'] = imm
+  from meltingpot_b200.shims import misc_shims  # pylint: disable=g-import-not-at-top
+  modules = None
+  for name in ('tree', 'chex', 'reactivex'):
+    if _missing(name):
+      modules = modules or misc_shims.build_modules()
+      sys.modules[name] = modules[name]
+      if name == 'reactivex':
+        sys.modules['reactivex.subject'] = modules['reactivex.subject']
+  if _missing('dmlab2d'):
+    # The FFI boundary itself: `dmlab2d.Lab2d` / `dmlab2d.Environment` (builder.py:179-187) backed by libmpengine.so.
+    from meltingpot_b200 import lab2d_env  # pylint: disable=g-import-not-at-top
+    for name, module in lab2d_env.build_modules().items():
+      sys.modules[name] = module

@@ -52,8 +52,9 @@ class TimeStep(NamedTuple):
     return self.step_type == StepType.LAST
 
 
-def restart(observation):
-  return TimeStep(StepType.FIRST, None, None, observation)
+def restart(observation, reward=None, discount=None):
+  # (the reference's wrapper tests pass `reward=` here: collective_reward_wrapper_reset_test.py:28-31)
+  return TimeStep(StepType.FIRST, reward, discount, observation)
 
 
 def transition(reward, observation, discount=1.0):

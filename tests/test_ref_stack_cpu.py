@@ -1,0 +1,78 @@
+"""The reference's own Python stack over this repo's `dmlab2d` boundary module (CPU: oracle backend; needs the checkout)."""
+
+import gzip
+import json
+import os
+import sys
+import unittest
+
+import numpy as np
+import pytest
+
+from meltingpot_b200 import compiler, lab2d_env
+from tests import ref_stack
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_reference = pytest.mark.skipif(compiler.reference_root() is None, reason='needs the reference checkout')
+
+
+def test_unflatten_inverts_flatten_and_str():
+  settings = {'levelName': 'clean_up', 'numPlayers': 7, 'spriteSize': 8, 'topology': 'BOUNDED', 'flag': True, 'none': None,
+              'simulation': {'map': '\nWW\nW \n', 'charPrefabMap': {'1': 'a', 'W': 'wall'}, 'rate': 0.05, 'tiny': 1e-05,
+                             'prefabs': {'wall': {'name': 'wall', 'components': [{'component': 'Transform', 'kwargs': {}},
+                                                                                 {'component': 'Appearance', 'kwargs': {'colors': [(1, 2, 3, 255)], 'names': ['Wall']}}]}},
+                             'gameObjects': [{'name': 'avatar', 'components': [{'component': 'Avatar', 'kwargs': {'index': 1, 'neg': -1}}]}]}}
+  flat = {k: str(v) for k, v in lab2d_env.flatten_args(settings).items()}
+  assert flat['simulation.prefabs.wall.components.2.kwargs.colors.1.4'] == '255'
+  back = lab2d_env.unflatten_args(flat)
+  want = json.loads(json.dumps(settings))  # tuples -> lists
+  del want['simulation']['prefabs']['wall']['components'][0]['kwargs']  # an empty dict has no flat key
+  del back['simulation']['prefabs']['wall']['components'][0]
+  del want['simulation']['prefabs']['wall']['components'][0]
+  assert back == want
+  assert isinstance(back['simulation']['charPrefabMap'], dict)  # digit keys, still a dict
+
+
+@needs_reference
+@pytest.mark.parametrize('name,players', [('clean_up', 7), ('territory__rooms', 9), ('coins', 2)])
+def test_reference_stack_reproduces_the_committed_fixture(name, players):
+  with open(os.path.join(ROOT, 'tests', 'golden', f'ref_stack_{name}.json')) as f:
+    want = json.load(f)
+  got = json.loads(json.dumps(ref_stack.run_reference_stack(name, players)))
+  got.pop('flat_settings')
+  assert got['class'] == 'meltingpot.utils.substrates.substrate.Substrate'  # the reference's class, not this repo's mirror
+  assert got == want
+
+
+@needs_reference
+def test_compiling_from_flattened_settings_equals_compiling_from_the_config():
+  # builder.py flattens the settings to "a.b.1.c" -> str for Lua (builder.py:55-67); lab2d_env un-flattens them. The blob
+  # compiled from the round-tripped settings must equal the one compiled from the config's own settings.
+  config = compiler.load_reference_config('clean_up')
+  settings = compiler._plain(config.lab2d_settings_builder(roles=('default',) * 7, config=config))  # pylint: disable=protected-access
+  flat = {k.replace('$', '.'): str(v) for k, v in lab2d_env.flatten_args(settings).items()}
+  back = lab2d_env.unflatten_args(flat)
+  assert compiler.compile_settings(back, config) == compiler.compile_settings(settings, config)
+
+
+@needs_reference
+@pytest.mark.parametrize('module', ['multiplayer_wrapper_test', 'discrete_action_wrapper_test', 'collective_reward_wrapper_test',
+                                    'collective_reward_wrapper_reset_test', 'observables_wrapper_test', 'reset_wrapper_test', 'base_test'])
+def test_reference_wrapper_unit_tests_pass_on_this_repos_dependency_shims(module):
+  # The reference's own wrapper tests (mocks of dmlab2d.Environment) run against this repo's dmlab2d / dm_env /
+  # immutabledict / reactivex stand-ins: the boundary module offers everything the wrappers touch.
+  import importlib
+  with ref_stack.reference_stack_on_oracle():
+    mod = importlib.import_module(f'meltingpot.utils.substrates.wrappers.{module}')
+    suite = unittest.defaultTestLoader.loadTestsFromModule(mod)
+    assert suite.countTestCases() > 0
+    result = unittest.TextTestRunner(stream=open(os.devnull, 'w'), verbosity=0).run(suite)
+    assert result.wasSuccessful(), [str(f[1])[-600:] for f in result.failures + result.errors][:2]
+
+
+@needs_reference
+def test_reference_import_leaves_no_stub_modules_behind():
+  compiler.load_reference_config('clean_up')
+  import meltingpot  # this repo's alias package, not a stub of the checkout
+  assert 'meltingpot_b200' in (meltingpot.__doc__ or '') and hasattr(meltingpot, 'substrate')
+  assert not [k for k in sys.modules if k.startswith('meltingpot.configs')]
