@@ -267,15 +267,13 @@ class Job:
       self.eng.step(self.actions[t])
       return
     # The state-transition kernel writes this rank's packed timestep rows into every rank's gathered buffer (peer
-    # stores over NVLink) as it produces them. The consumer-side wait for the other ranks' rows is a one-warp kernel
-    # on a side stream; it is resident next to the persistent render CTAs, so it costs the step nothing.
-    import torch
-    self.eng.step_state(self.actions[t])
+    # stores over NVLink) as it produces them; the two kernels of the step stay back to back on the main stream (the
+    # renderer's prologue overlaps the transition's tail). The consumer-side wait for the other ranks' rows is a
+    # one-warp kernel on a side stream, off the critical path.
+    self.eng.step(self.actions[t])
     self.stepped.record(self.stream)
     self.side.wait_event(self.stepped)
-    with torch.cuda.stream(self.side):
-      self.eng.exchange_wait(self.side)
-    self.eng.render()
+    self.eng.exchange_wait(self.side)
 
   def join(self):
     if self.side is not None:
@@ -406,6 +404,51 @@ def run_e2e(job, n_e, dist, images=True):
   return dt, h2d, d2h, checksum
 
 
+def run_gather_obs(job, n_g, dist, world, rank):
+  """Steps with the renderer also delivering every strip into every rank's stacked observation buffer (mp_gather_obs_*,
+  TMA bulk stores over NVLink peer mappings). Returns (ms per step, bytes each rank sends to its peers per step)."""
+  import torch
+  eng = job.eng
+  if world > 1:
+    from meltingpot_b200 import distributed
+    distributed.connect_gather_obs(eng)
+  else:
+    ptr, _ = eng.gather_obs_create(0, 1)
+    eng.gather_obs_connect([ptr])
+  for t in range(3):
+    job.step(t)
+  job.join()
+  eng.gather_obs_wait()
+  torch.cuda.synchronize()
+  if dist is not None:
+    dist.barrier()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev0.record(job.stream)
+  for t in range(n_g):
+    job.step(3 + t)
+  job.join()
+  eng.gather_obs_wait()  # the consumer-side wait for every rank's last delivery closes the timed region
+  ev1.record(job.stream)
+  torch.cuda.synchronize()
+  if dist is not None:
+    dist.barrier()
+  ms = ev0.elapsed_time(ev1) / n_g
+  ok = None
+  if world > 1:  # what arrived from the right neighbour equals what it holds (checked through an NCCL all-gather of hashes)
+    rgb, wrgb = eng.gathered_observations()
+    B = job.B
+    mine = torch.stack([eng.rgb.to(torch.int64).sum(), eng.world_rgb.to(torch.int64).sum()])
+    every = torch.empty((world, 2), dtype=torch.int64, device=mine.device)
+    dist.all_gather_into_tensor(every, mine)
+    got = torch.stack([torch.stack([rgb[r * B:(r + 1) * B].to(torch.int64).sum(), wrgb[r * B:(r + 1) * B].to(torch.int64).sum()]) for r in range(world)])
+    flag = torch.tensor([1 if bool((got == every).all()) else 0], device=mine.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ok = 'ok' if int(flag.item()) == 1 else 'MISMATCH'
+  eng.gather_obs_enable(False)
+  obs_bytes = eng.rgb.numel() + eng.world_rgb.numel()
+  return ms, obs_bytes * max(world - 1, 0), obs_bytes, ok
+
+
 def run_b200(args, rank, world, local_rank):
   numa = bind_to_gpu_numa_node(local_rank)
   import torch
@@ -434,7 +477,7 @@ def run_b200(args, rank, world, local_rank):
   sampler = ClockSampler(local_rank) if rank == 0 else None
   per_job, elapsed_ms, launches, env_steps = [], 0.0, 0, 0
   shard = None
-  e2e = e2e_scalars = None
+  e2e = e2e_scalars = gather = None
   first_job = None
   for ji, (name, players) in enumerate(my_jobs):
     job = Job(name, players, B, rank, world, local_rank, K, Wm, exchange=single)
@@ -469,6 +512,16 @@ def run_b200(args, rank, world, local_rank):
         dt_s = max_over_ranks(dt_s)
         e2e_scalars = {'value': world * B * n_s / dt_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d_s, 'd2h_bytes_per_step': d2h_s,
                        'steps': n_s, 'api': 'same calls with NULL image pointers (images stay in HBM for a GPU-resident consumer)'}
+        if args.gather_obs:
+          n_g = max(4, min(K, 24))
+          ms_g, sent, obs_bytes, ok = run_gather_obs(job, n_g, dist, world, rank)
+          ms_g = max_over_ranks(ms_g)
+          gather = {'value': world * B / (ms_g * 1e-3), 'unit': UNIT, 'ms_per_step': ms_g, 'steps': n_g,
+                    'obs_bytes_per_rank_per_step': obs_bytes, 'nvlink_bytes_sent_per_rank_per_step': sent,
+                    'nvlink_gbs_per_gpu_egress': sent / (ms_g * 1e-3) / 1e9, 'nvlink_peak_gbs_per_direction': 900.0,
+                    'frac_of_nvlink': sent / (ms_g * 1e-3) / 1e9 / 900.0, 'check': ok,
+                    'how': 'k_render<GATHER> hands every finished strip to one TMA bulk store per rank (peer memory over NVLink / NVSwitch) '
+                           'next to the local one; two stacked buffers per rank (slot = step parity), flag wait kernel on the consumer side'}
     job.eng.close()
     del job
   if not single and dist is not None:
@@ -518,6 +571,8 @@ def run_b200(args, rank, world, local_rank):
       line['e2e_scalars_only'] = e2e_scalars
     if shard is not None:
       line['shard_check'] = shard
+    if gather is not None:
+      line['gather_obs'] = gather
     if not args.no_cpu_baseline and world == 1:
       line['cpu_baseline'] = cpu_baseline(cfg['jobs'], seconds=args.ref_seconds)
     _emit(line)
@@ -547,6 +602,7 @@ def main():
   ap.add_argument('--e2e-steps', type=int, default=40)
   ap.add_argument('--ref-seconds', type=float, default=15.0, help='CPU arm / cpu_baseline: seconds of oracle work to time')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--gather-obs', action='store_true', help='also measure steps with the stacked-observation gather over NVLink')
   args = ap.parse_args()
   rank = int(os.environ.get('RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -87,6 +87,13 @@ typedef struct mp_buffers {
    * global env order (rank r's envs at rows [r * B, (r + 1) * B)); slot (step & 1) holds the most recent step. */
   double* gathered;
   int32_t gathered_world;
+  /* After mp_gather_obs_create: the stacked observations of EVERY rank's envs in global env order, two slots of
+   * gathered_obs_slot_bytes bytes each (slot = parity of the render sequence number, mp_gather_obs_slot):
+   * gathered_rgb u8 [world * B][P][rgb_h][rgb_w][3] and gathered_world_rgb u8 [world * B][world_h][world_w][3] of slot
+   * 0; add gathered_obs_slot_bytes for slot 1. */
+  uint8_t* gathered_rgb;
+  uint8_t* gathered_world_rgb;
+  uint64_t gathered_obs_slot_bytes;
 } mp_buffers;
 
 /* Replaces dmlab2d.Lab2d(...) + dmlab2d.Environment(...) (builder.py:182-187) for `num_envs`
@@ -172,6 +179,19 @@ int mp_enable_peer_access(int device, int peer_device);
 int mp_exchange_connect(mp_handle h, void* const* peer_blocks);
 int mp_exchange_wait(mp_handle h, void* stream);
 int mp_exchange_slot(mp_handle h, int* slot, uint64_t* step);
+
+/* Stacked OBSERVATIONS across GPUs -- the all-gather BASELINE.json's north_star names ("an NCCL all-gather over NVLink
+ * only to return a single stacked observation tensor"), fused into the renderer: with gathering on, k_render hands
+ * every finished strip in its shared-memory staging buffer to one TMA bulk store per rank (cp.async.bulk over NVLink
+ * peer mappings) in addition to the local one, so the pixels are composed once and travel while the next strips are
+ * being drawn -- no collective kernel, no second pass over HBM. NVLink-bound by construction: every rank receives
+ * (world - 1) x its own observation bytes per step. Same create / IPC / connect / wait / slot protocol as mp_exchange_*;
+ * mp_gather_obs_enable switches the extra stores on and off (they start on after connect). */
+int mp_gather_obs_create(mp_handle h, int rank, int world, void** block, uint64_t* block_bytes);
+int mp_gather_obs_connect(mp_handle h, void* const* peer_blocks);
+int mp_gather_obs_enable(mp_handle h, int on);
+int mp_gather_obs_wait(mp_handle h, void* stream);
+int mp_gather_obs_slot(mp_handle h, int* slot, uint64_t* step);
 
 /* Number of kernels this engine has launched since creation (all streams). */
 int mp_launch_count(mp_handle h, uint64_t* out);

@@ -139,7 +139,15 @@ struct State {
   unsigned long long x_step;               // sequence number of this launch; slot = x_step & 1
   double* x_gathered[MP_MAX_PEERS];
   unsigned long long* x_flags[MP_MAX_PEERS];
-  unsigned int* x_counter;                 // local: env warps that have published in this launch
+  int x_raise;                             // render launches only: 1 = raise this step's flags in the prologue
+  // Stacked observations across GPUs (mp_gather_obs_*): when g_world > 0 the renderer stores every strip not only to
+  // this rank's rgb / world_rgb but also, straight from its staging buffer (TMA bulk stores over NVLink peer mappings),
+  // into this rank's slab of EVERY rank's stacked buffer. g_rgb / g_wrgb already point at (slot, x_rank's slab).
+  int g_world;
+  unsigned long long g_step;               // sequence number of this render launch; slot = g_step & 1
+  uint8_t* g_rgb[MP_MAX_PEERS];
+  uint8_t* g_wrgb[MP_MAX_PEERS];
+  const unsigned long long* g_flags;       // local flags[r] = last render rank r has fully delivered here
 };
 
 // Events of the current step (the reference's events:add calls on the hot path). Types follow
@@ -206,13 +214,20 @@ __device__ __forceinline__ bool wrap_or_reject(const Tables& T, int& x, int& y) 
   return x >= 0 && x < T.W && y >= 0 && y < T.H;
 }
 
-// Called by every env warp at the end of a state-transition launch (also by envs a masked reset left untouched, so
+// Called by every env warp at the end of a state-transition launch (envs a masked reset left untouched publish too, so
 // that the slot of this step is complete). Lane i < P + 2 forwards element i of the env's packed timestep row
-// (reward[0..P), discount, step type) to every rank's gathered buffer with plain stores through the peer mapping:
-// the "all-gather" is P + 2 remote stores per env and rank, issued by the kernel that produced the values, with no
-// collective kernel and no extra launch. The last warp of the grid to finish raises flags[x_rank] = x_step on every
-// rank (release at system scope), which k_exchange_wait polls on the consumer side.
-__device__ __forceinline__ void exchange_publish(const Tables& T, const State& S, int b, int lane) {
+// (reward[0..P), discount, step type) to every rank's gathered buffer with plain stores through the peer mapping: the
+// "all-gather" is P + 2 remote stores per env and rank, issued by the kernel that produced the values, with no
+// collective kernel. Nothing here fences: a system-scope fence per warp (or CTA) costs the launch ~15 us (measured).
+// The kernel boundary already orders these stores, so the flag that tells the other ranks "step s of rank r is
+// complete" is raised by ONE thread of the kernel that follows in the stream (exchange_raise: the renderer's
+// prologue after griddepcontrol.wait, or k_exchange_raise when no render follows).
+// Issued at the top of the launch so that the flow-control read below is off the warp's critical path.
+__device__ __forceinline__ unsigned long long exchange_peek(const State& S, int lane) {
+  if (S.x_world == 0 || lane >= S.x_world) return ~0ull;
+  return *(const volatile unsigned long long*)(S.x_flags[S.x_rank] + lane);
+}
+__device__ __forceinline__ void exchange_publish(const Tables& T, const State& S, int b, int lane, unsigned long long seen) {
   if (S.x_world == 0) return;
   __syncwarp();
   // Flow control: slot (x_step & 1) still holds step x_step - 2 on every rank. A rank has finished with it (its
@@ -220,12 +235,8 @@ __device__ __forceinline__ void exchange_publish(const Tables& T, const State& S
   // The slowest rank never waits on a faster one, hence no cycle; in steady state the flags were raised a whole
   // render ago and this is one local read.
   if (lane < S.x_world && S.x_step > 1ull) {
-    const unsigned long long* f = S.x_flags[S.x_rank] + lane;
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-      if (v + 1ull < S.x_step) __nanosleep(100);
-    } while (v + 1ull < S.x_step);
+    const volatile unsigned long long* f = S.x_flags[S.x_rank] + lane;
+    while (seen + 1ull < S.x_step) { __nanosleep(100); seen = *f; }
   }
   __syncwarp();
   const int n = T.P + 2;
@@ -234,19 +245,21 @@ __device__ __forceinline__ void exchange_publish(const Tables& T, const State& S
     const size_t off = ((size_t)(S.x_step & 1ull) * S.x_world * S.B + (size_t)S.x_rank * S.B + b) * n + lane;
     for (int r = 0; r < S.x_world; ++r) S.x_gathered[r][off] = v;
   }
-  __syncwarp();
-  if (lane == 0) {
-    __threadfence_system();  // this warp's remote stores are performed before its arrival is counted
-    const unsigned int arrived = atomicAdd(S.x_counter, 1u);
-    if (arrived == (unsigned int)S.B - 1u) {
-      __threadfence_system();
-      *S.x_counter = 0u;  // (the next launch on this engine is stream-ordered after this kernel)
-      for (int r = 0; r < S.x_world; ++r) {
-        unsigned long long* f = S.x_flags[r] + S.x_rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(S.x_step) : "memory");
-      }
-    }
+}
+
+// By one thread, after the state-transition kernel of step x_step has completed (kernel boundary: its stores, the
+// remote ones included, have been performed before a dependent kernel runs): flags[x_rank] = x_step on every rank.
+// A plain system-scope store is enough here and a release (= another system fence, ~5 us that would hold up the
+// renderer team this thread belongs to) is not needed: the data is already in place.
+__device__ __forceinline__ void exchange_raise(const State& S) {
+  for (int r = 0; r < S.x_world; ++r) {
+    unsigned long long* f = S.x_flags[r] + S.x_rank;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(S.x_step) : "memory");
   }
+}
+__global__ void __launch_bounds__(32) k_exchange_raise(State S) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) exchange_raise(S);
 }
 
 // One warp: lane r < world waits until rank r has published step `step` into this rank's gathered buffer. Small
@@ -259,5 +272,13 @@ __global__ void __launch_bounds__(32) k_exchange_wait(const unsigned long long* 
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + lane) : "memory");
       if (v < step) __nanosleep(200);
     } while (v < step);
+  }
+}
+
+// After a gathering render has completed: flags[rank] = step on every rank (same protocol as exchange_raise).
+__global__ void __launch_bounds__(32) k_gather_raise(unsigned long long* const* flags, int world, int rank, unsigned long long step) {
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags[threadIdx.x] + rank), "l"(step) : "memory");
   }
 }

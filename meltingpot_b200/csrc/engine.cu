@@ -213,11 +213,20 @@ struct mp_engine {
   uint8_t* x_block = nullptr;      // [flags: MP_EXCHANGE_HEADER bytes][gathered f64 [2][world * B][P + 2]]
   uint64_t x_block_bytes = 0;
   unsigned long long x_seq = 0;   // incremented by every state-transition launch once the exchange is connected
+  bool x_pending_raise = false;   // a state transition published and the flags are to be raised by the render that follows
   int32_t* d_avatar_dbg = nullptr;
   uint64_t launches = 0;
   int sm_count = 0;
   size_t step_smem = 0;
   void (*render_fn)(Tables, State, RenderPlan, uint32_t) = nullptr;
+  void (*render_gather_fn)(Tables, State, RenderPlan, uint32_t) = nullptr;
+  // mp_gather_obs_*: this rank's stacked-observation block [flags 256 B][2 slots][rgb of all ranks | world_rgb of all ranks]
+  uint8_t* g_block = nullptr;
+  uint64_t g_block_bytes = 0, g_slot_bytes = 0, g_world_off = 0;
+  uint8_t* g_peer[MP_MAX_PEERS] = {};
+  unsigned long long** d_g_flag_ptrs = nullptr;  // device array of every rank's flags pointer (for k_gather_raise)
+  int g_world = 0, g_rank = 0;
+  unsigned long long g_seq = 0;
   uint64_t algo_bytes = 0, render_bytes = 0;
   std::vector<uint8_t> host_pair, host_sflags;  // kept for mp_debug_render_tables
   int black_sprite = -1;
@@ -690,7 +699,16 @@ int build_plan(mp_engine* E) {
   return MP_OK;
 }
 
-int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int mode, cudaStream_t st) {
+int raise_flags(mp_engine* E, cudaStream_t st) {
+  E->x_pending_raise = false;
+  k_exchange_raise<<<1, 32, 0, st>>>(E->S);
+  ++E->launches;
+  CUDA_TRY(cudaGetLastError());
+  return MP_OK;
+}
+
+// `render_follows`: the caller launches the renderer next on the same stream; it raises the exchange flags.
+int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int mode, cudaStream_t st, bool render_follows = true) {
   const int blocks = (E->B + 3) / 4;
   if (E->S.x_world) E->S.x_step = ++E->x_seq;
   void (*fn)(Tables, State, const int32_t*, const uint8_t*, int) =
@@ -703,13 +721,19 @@ int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, E->T, E->S, actions, mask, mode));
+  if (E->S.x_world) {
+    E->x_pending_raise = true;
+    if (!render_follows) { ++E->launches; return raise_flags(E, st); }
+  }
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;
 }
 
 int launch_render(mp_engine* E, cudaStream_t st) {
-  if (!(E->flags & (MP_FLAG_RENDER_WORLD | MP_FLAG_RENDER_PLAYERS))) return MP_OK;
+  if (!(E->flags & (MP_FLAG_RENDER_WORLD | MP_FLAG_RENDER_PLAYERS))) return E->x_pending_raise ? raise_flags(E, st) : MP_OK;
+  E->S.x_raise = E->x_pending_raise ? 1 : 0;
+  E->x_pending_raise = false;
   const int blocks = std::min(E->B, E->sm_count);  // every CTA has at least one env (balanced rounds + cooperative tail)
   RenderPlan R = E->R;
   const Tables& T = E->T;
@@ -727,7 +751,21 @@ int launch_render(mp_engine* E, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, E->render_fn, E->T, E->S, R, E->flags));
+  const bool gather = E->g_world > 0 && E->S.g_world > 0;
+  if (gather) {
+    E->S.g_step = ++E->g_seq;
+    const size_t slot = (size_t)(E->g_seq & 1ull) * E->g_slot_bytes;
+    for (int r = 0; r < E->g_world; ++r) {
+      uint8_t* base = E->g_peer[r] + MP_EXCHANGE_HEADER + slot;
+      E->S.g_rgb[r] = base + (size_t)E->g_rank * E->B * T.P * R.player_bytes;
+      E->S.g_wrgb[r] = base + E->g_world_off + (size_t)E->g_rank * E->B * R.world_bytes;
+    }
+  }
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, gather ? E->render_gather_fn : E->render_fn, E->T, E->S, R, E->flags));
+  if (gather) {
+    k_gather_raise<<<1, 32, 0, st>>>(E->d_g_flag_ptrs, E->g_world, E->g_rank, E->g_seq);
+    ++E->launches;
+  }
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;
@@ -837,10 +875,10 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   E->step_smem = E->family == MPB_FAMILY_TERRITORY ? territory_scratch_bytes(T) : warp_scratch_bytes(T);
   {  // cells per lane per strip: ceil(view_w / 4) for player rows, ceil(W / 8) for world half-rows
     const int ncp = (E->R.view_w + 3) / 4, ncw = (T.W + (32 >> E->R.wstrip_log2) - 1) / (32 >> E->R.wstrip_log2);
-    if (ncp <= 3 && ncw <= 3) E->render_fn = k_render<3, 3>;
-    else if (ncp <= 3 && ncw <= 4) E->render_fn = k_render<3, 4>;
-    else if (ncp <= 3 && ncw <= 5) E->render_fn = k_render<3, 5>;
-    else if (ncp <= 4 && ncw <= 5) E->render_fn = k_render<4, 5>;
+    if (ncp <= 3 && ncw <= 3) { E->render_fn = k_render<3, 3, false>; E->render_gather_fn = k_render<3, 3, true>; }
+    else if (ncp <= 3 && ncw <= 4) { E->render_fn = k_render<3, 4, false>; E->render_gather_fn = k_render<3, 4, true>; }
+    else if (ncp <= 3 && ncw <= 5) { E->render_fn = k_render<3, 5, false>; E->render_gather_fn = k_render<3, 5, true>; }
+    else if (ncp <= 4 && ncw <= 5) { E->render_fn = k_render<4, 5, false>; E->render_gather_fn = k_render<4, 5, true>; }
     else { mp_destroy(E); return fail(MP_E_UNSUPPORTED, "view of %d cells / map of %d cells wide (max 16 / 40)", E->R.view_w, T.W); }
     // lane -> cell dealing (see make_lane_map_cells / make_lane_map): whole cells per lane group with the cell order chosen
     // to minimise store bank conflicts by default; the fully conflict-free scattered colouring or the plain order for A/B.
@@ -859,6 +897,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   // The attribute belongs to the kernel function, not to this handle: engines that share an instantiation must not
   // lower each other's limit, so the renderer always gets the opt-in maximum and the step kernels only ever raise theirs.
   cudaError_t ce = cudaFuncSetAttribute(E->render_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmemLimit);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(E->render_gather_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmemLimit);
   {
     static int step_smem_max[MP_MAX_DEVICES] = {};
     const int need = (int)(E->step_smem * 4);
@@ -916,7 +955,7 @@ int mp_reset(mp_handle h, const uint8_t* env_mask, void* stream) {
 int mp_step_state(mp_handle h, const int32_t* actions, void* stream) {
   if (!h || !actions) return fail(MP_E_INVALID, "mp_step_state: null handle or actions");
   DeviceGuard guard(h->device);
-  return launch_state(h, actions, nullptr, 0, (cudaStream_t)stream);
+  return launch_state(h, actions, nullptr, 0, (cudaStream_t)stream, /*render_follows=*/false);
 }
 
 int mp_render(mp_handle h, void* stream) {
@@ -1035,7 +1074,7 @@ int mp_exchange_create(mp_handle h, int rank, int world, void** block, uint64_t*
   const size_t n = (size_t)2 * world * h->B * (h->T.P + 2);
   int rc;
   // one allocation: flags (MP_EXCHANGE_HEADER bytes) then gathered, so that one IPC handle shares both
-  if ((rc = h->alloc(MP_EXCHANGE_HEADER + n * sizeof(double), &h->x_block)) || (rc = h->alloc((size_t)4, &h->S.x_counter))) return rc;
+  if ((rc = h->alloc(MP_EXCHANGE_HEADER + n * sizeof(double), &h->x_block))) return rc;
   h->x_block_bytes = MP_EXCHANGE_HEADER + n * sizeof(double);
   h->S.x_rank = rank;  // x_world stays 0 (exchange off) until mp_exchange_connect
   h->buffers.gathered = reinterpret_cast<double*>(h->x_block + MP_EXCHANGE_HEADER); h->buffers.gathered_world = world;
@@ -1098,6 +1137,71 @@ int mp_exchange_connect(mp_handle h, void* const* peer_blocks) {
     h->S.x_gathered[r] = reinterpret_cast<double*>(static_cast<uint8_t*>(peer_blocks[r]) + MP_EXCHANGE_HEADER);
   }
   h->S.x_world = world;
+  return MP_OK;
+}
+
+// ---- stacked observations across GPUs -------------------------------------------------------------------------------
+int mp_gather_obs_create(mp_handle h, int rank, int world, void** block, uint64_t* block_bytes) {
+  if (!h || world < 1 || world > MP_MAX_PEERS || rank < 0 || rank >= world) return fail(MP_E_INVALID, "mp_gather_obs_create: rank %d / world %d (max %d ranks)", rank, world, MP_MAX_PEERS);
+  if (h->g_block) return fail(MP_E_INVALID, "mp_gather_obs_create: already created for this handle");
+  DeviceGuard guard(h->device);
+  const size_t rgb_all = (size_t)world * h->B * h->T.P * h->R.player_bytes, world_all = (size_t)world * h->B * h->R.world_bytes;
+  h->g_world_off = rgb_all;
+  h->g_slot_bytes = (rgb_all + world_all + 255) / 256 * 256;
+  h->g_block_bytes = MP_EXCHANGE_HEADER + 2 * h->g_slot_bytes;
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, h->g_block_bytes));  // (not zeroed: gigabytes; only the flags header is)
+  h->allocs.push_back(p);
+  h->g_block = static_cast<uint8_t*>(p);
+  CUDA_TRY(cudaMemset(p, 0, MP_EXCHANGE_HEADER));
+  CUDA_TRY(cudaDeviceSynchronize());
+  h->g_world = world; h->g_rank = rank;
+  h->buffers.gathered_rgb = h->g_block + MP_EXCHANGE_HEADER;
+  h->buffers.gathered_world_rgb = h->g_block + MP_EXCHANGE_HEADER + h->g_world_off;
+  h->buffers.gathered_obs_slot_bytes = h->g_slot_bytes;
+  if (block) *block = h->g_block;
+  if (block_bytes) *block_bytes = h->g_block_bytes;
+  return MP_OK;
+}
+
+int mp_gather_obs_connect(mp_handle h, void* const* peer_blocks) {
+  if (!h || !peer_blocks) return fail(MP_E_INVALID, "mp_gather_obs_connect: null argument");
+  if (!h->g_block) return fail(MP_E_INVALID, "mp_gather_obs_connect: call mp_gather_obs_create first");
+  if (peer_blocks[h->g_rank] != h->g_block) return fail(MP_E_INVALID, "mp_gather_obs_connect: entry %d must be this rank's own block", h->g_rank);
+  DeviceGuard guard(h->device);
+  std::vector<unsigned long long*> ptrs(MP_MAX_PEERS, nullptr);
+  for (int r = 0; r < h->g_world; ++r) {
+    if (!peer_blocks[r]) return fail(MP_E_INVALID, "mp_gather_obs_connect: null pointer for rank %d", r);
+    h->g_peer[r] = static_cast<uint8_t*>(peer_blocks[r]);
+    ptrs[r] = reinterpret_cast<unsigned long long*>(peer_blocks[r]);
+  }
+  int rc = h->alloc((size_t)MP_MAX_PEERS, &h->d_g_flag_ptrs);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpy(h->d_g_flag_ptrs, ptrs.data(), MP_MAX_PEERS * sizeof(void*), cudaMemcpyHostToDevice));
+  h->S.g_flags = reinterpret_cast<const unsigned long long*>(h->g_block);
+  h->S.g_world = h->g_world;
+  return MP_OK;
+}
+
+int mp_gather_obs_enable(mp_handle h, int on) {
+  if (!h || !h->g_block || !h->d_g_flag_ptrs) return fail(MP_E_INVALID, "mp_gather_obs_enable: not connected");
+  h->S.g_world = on ? h->g_world : 0;
+  return MP_OK;
+}
+
+int mp_gather_obs_wait(mp_handle h, void* stream) {
+  if (!h || !h->g_block) return fail(MP_E_INVALID, "mp_gather_obs_wait: not created");
+  DeviceGuard guard(h->device);
+  k_exchange_wait<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(h->g_block), h->g_world, h->g_seq);
+  ++h->launches;
+  CUDA_TRY(cudaGetLastError());
+  return MP_OK;
+}
+
+int mp_gather_obs_slot(mp_handle h, int* slot, uint64_t* step) {
+  if (!h) return fail(MP_E_INVALID, "null handle");
+  if (slot) *slot = (int)(h->g_seq & 1ull);
+  if (step) *step = h->g_seq;
   return MP_OK;
 }
 

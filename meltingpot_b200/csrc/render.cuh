@@ -237,7 +237,8 @@ struct ViewerInfo {  // per player, refreshed once per env
 // a half / quarter cell row (4 / 2 pixel rows) of WORLD.RGB -- compose them into a warp-private staging slot and
 // hand the slot to the TMA store engine. Two team barriers per env; everything else is warp-local.
 // Each lane handles NC cells per strip with the loads of all NC cells issued before any is packed.
-template <int NCP, int NCW>
+// GATHER: also deliver every strip into every rank's stacked observation buffer (State::g_*).
+template <int NCP, int NCW, bool GATHER>
 __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, State S, RenderPlan R, uint32_t flags) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);  // [0] atlas, [1 + team] grid
@@ -291,6 +292,13 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
   // Everything above reads only static tables: with a programmatic dependent launch it overlaps the tail of the
   // state-transition kernel. The env state (grid, avatars) may be read only after this point.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (S.x_raise && blockIdx.x == 0 && tid == 32) exchange_raise(S);  // the step's rows are complete on every rank: tell them
+  if (GATHER && tid == 64 && S.g_step > 1ull) {
+    // flow control of the stacked buffers: slot (g_step & 1) holds render g_step - 2; a rank is done with it once it has
+    // delivered render g_step - 1 (its consumers are stream-ordered before that launch)
+    for (int r = 0; r < S.g_world; ++r)
+      while (*(const volatile unsigned long long*)(S.g_flags + r) + 1ull < S.g_step) __nanosleep(200);
+  }
   if (ttid == 0 && rounds > 0) {
     mbar_expect_tx(gbar, (uint32_t)R.grid_bytes);
     bulk_load(s_grid, S.grid + (size_t)first * T.L * T.cells_pad, (uint32_t)R.grid_bytes, gbar);
@@ -392,7 +400,11 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
         }
         if (!(flags & 128u)) fence_async_smem();  // make this lane's writes visible to the async (TMA) proxy
         __syncwarp();
-        if (lane == 0 && !(flags & 32u)) bulk_store(S.rgb + ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * R.pitem_bytes, buf, (uint32_t)R.pitem_bytes, store_policy);
+        if (lane == 0 && !(flags & 32u)) {
+          const size_t off = ((size_t)b * T.P + p) * R.player_bytes + (size_t)cy * R.pitem_bytes;
+          bulk_store(S.rgb + off, buf, (uint32_t)R.pitem_bytes, store_policy);
+          if (GATHER) for (int r = 0; r < S.g_world; ++r) bulk_store(S.g_rgb[r] + off, buf, (uint32_t)R.pitem_bytes, store_policy);
+        }
       } else {
         const int wi = item - R.n_player_items, wy = wi >> (3 - wlog);
         const int py = ((wi & ((8 >> wlog) - 1)) << wlog) | (lane & (wrows - 1));
@@ -416,12 +428,16 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
         }
         if (!(flags & 128u)) fence_async_smem();
         __syncwarp();
-        if (lane == 0 && !(flags & 32u)) bulk_store(S.world_rgb + (size_t)b * R.world_bytes + (size_t)wi * R.witem_bytes, buf, (uint32_t)R.witem_bytes, store_policy);
+        if (lane == 0 && !(flags & 32u)) {
+          const size_t off = (size_t)b * R.world_bytes + (size_t)wi * R.witem_bytes;
+          bulk_store(S.world_rgb + off, buf, (uint32_t)R.witem_bytes, store_policy);
+          if (GATHER) for (int r = 0; r < S.g_world; ++r) bulk_store(S.g_wrgb[r] + off, buf, (uint32_t)R.witem_bytes, store_policy);
+        }
       }
     }
     group_sync(bar_id, gthreads);  // every warp is done with s_rec / s_view
     if (gtid == 0) *next_ctr = 0;
     // (the reset is ordered before the next env's item loop by the group barrier after its cell pass)
   }
-  if (lane == 0) bulk_wait_read<0>();
+  if (lane == 0) { if (GATHER) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); else bulk_wait_read<0>(); }  // (remote stores: wait for completion, not just for the source reads)
 }

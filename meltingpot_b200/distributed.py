@@ -73,6 +73,21 @@ def connect_exchange(eng, group=None) -> None:
   dist.barrier(group=group)  # nobody publishes before everyone is mapped
 
 
+def connect_gather_obs(eng, group=None) -> None:
+  """Wires `eng` into the stacked-observation gather (mp_gather_obs_*): from then on its renderer also delivers every
+  strip into every rank's stacked buffer over NVLink. torch.distributed only carries the IPC handles, once."""
+  import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+  from meltingpot_b200 import engine as engine_lib  # pylint: disable=g-import-not-at-top
+  rank, world = dist.get_rank(group), dist.get_world_size(group)
+  ptr, _ = eng.gather_obs_create(rank, world)
+  mine = engine_lib.ipc_export(ptr)
+  everyone = [None] * world
+  dist.all_gather_object(everyone, mine, group=group)
+  blocks = [ptr if r == rank else engine_lib.ipc_open(eng.device, everyone[r][0], everyone[r][1]) for r in range(world)]
+  eng.gather_obs_connect(blocks)
+  dist.barrier(group=group)
+
+
 class ShardedSubstrate:
   """One rank's shard of a globally indexed batch of env instances."""
 

@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     'mp_reset_host', 'mp_launch_count', 'mp_algorithmic_bytes', 'mp_debug_render_tables', 'mp_debug_render_plan', 'mp_state_size', 'mp_state_save', 'mp_state_load',
     'mp_step_host_async', 'mp_wait', 'mp_exchange_create', 'mp_ipc_export', 'mp_ipc_open', 'mp_enable_peer_access',
     'mp_exchange_connect', 'mp_exchange_wait', 'mp_exchange_slot', 'mp_debug_lane_map',
+    'mp_gather_obs_create', 'mp_gather_obs_connect', 'mp_gather_obs_enable', 'mp_gather_obs_wait', 'mp_gather_obs_slot',
     'mp_last_error', 'mp_version',
 )
 
@@ -46,6 +47,7 @@ class MpBuffers(ctypes.Structure):
       ('events', ctypes.c_void_p), ('event_count', ctypes.c_void_p), ('max_events', ctypes.c_int32),
       ('scalar_block', ctypes.c_void_p), ('scalar_block_bytes', ctypes.c_uint64),
       ('gathered', ctypes.c_void_p), ('gathered_world', ctypes.c_int32),
+      ('gathered_rgb', ctypes.c_void_p), ('gathered_world_rgb', ctypes.c_void_p), ('gathered_obs_slot_bytes', ctypes.c_uint64),
   ]
 
 
@@ -101,6 +103,11 @@ def load_library() -> ctypes.CDLL:
   lib.mp_exchange_connect.argtypes = [vp, ctypes.POINTER(vp)]
   lib.mp_exchange_wait.argtypes = [vp, vp]
   lib.mp_exchange_slot.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint64)]
+  lib.mp_gather_obs_create.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_uint64)]
+  lib.mp_gather_obs_connect.argtypes = [vp, ctypes.POINTER(vp)]
+  lib.mp_gather_obs_enable.argtypes = [vp, ctypes.c_int]
+  lib.mp_gather_obs_wait.argtypes = [vp, vp]
+  lib.mp_gather_obs_slot.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint64)]
   lib.mp_debug_lane_map.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_uint32)]
   lib.mp_last_error.restype = ctypes.c_char_p
   lib.mp_version.restype = ctypes.c_char_p
@@ -207,7 +214,7 @@ class Engine:
 
   # -- lifecycle -----------------------------------------------------------------
   _VIEWS = ('rgb', 'world_rgb', 'reward', 'discount', 'step_type', 'scalar_obs', 'avatar_state', 'grid',
-            'timestep_packed', 'events', 'event_count', 'gathered')
+            'timestep_packed', 'events', 'event_count', 'gathered', 'gathered_rgb', 'gathered_world_rgb')
 
   def close(self) -> None:
     """Drops this object's references. mp_destroy runs when the last tensor view handed out has been released too
@@ -347,6 +354,40 @@ class Engine:
   def gathered_timestep(self):
     """The stacked [world * B, P + 2] timestep rows of the most recent step (call exchange_wait first)."""
     return self.gathered[self.exchange_slot()[0]]
+
+  # -- stacked observations across GPUs (mp_gather_obs_*) ----------------------------------
+  def gather_obs_create(self, rank: int, world: int):
+    """Allocates this rank's stacked-observation block; returns (device pointer, bytes)."""
+    ptr, n = ctypes.c_void_p(), ctypes.c_uint64(0)
+    _check(self._lib.mp_gather_obs_create(self._h, int(rank), int(world), ctypes.byref(ptr), ctypes.byref(n)))
+    bufs = MpBuffers()
+    _check(self._lib.mp_get_buffers(self._h, ctypes.byref(bufs)))
+    self.buffers = bufs
+    torch = self._torch
+    dev = torch.device('cuda', self.device)
+    B, P = self.num_envs, self.num_players
+    slot = int(bufs.gathered_obs_slot_bytes)
+    self.gathered_rgb = [torch.as_tensor(_CudaView(bufs.gathered_rgb + k * slot, (world * B, P, bufs.rgb_h, bufs.rgb_w, 3), '|u1', self._owner),
+                                         device=dev, dtype=torch.uint8) for k in range(2)]
+    self.gathered_world_rgb = [torch.as_tensor(_CudaView(bufs.gathered_world_rgb + k * slot, (world * B, bufs.world_h, bufs.world_w, 3), '|u1', self._owner),
+                                               device=dev, dtype=torch.uint8) for k in range(2)]
+    return int(ptr.value), int(n.value)
+
+  def gather_obs_connect(self, peer_blocks) -> None:
+    arr = (ctypes.c_void_p * len(peer_blocks))(*[ctypes.c_void_p(int(p)) for p in peer_blocks])
+    _check(self._lib.mp_gather_obs_connect(self._h, arr))
+
+  def gather_obs_enable(self, on: bool) -> None:
+    _check(self._lib.mp_gather_obs_enable(self._h, int(bool(on))))
+
+  def gather_obs_wait(self, stream=None) -> None:
+    _check(self._lib.mp_gather_obs_wait(self._h, self._stream(stream)))
+
+  def gathered_observations(self):
+    """(rgb [world * B, P, h, w, 3], world_rgb [world * B, H, W, 3]) of the most recent render (gather_obs_wait first)."""
+    slot = ctypes.c_int(0)
+    _check(self._lib.mp_gather_obs_slot(self._h, ctypes.byref(slot), None))
+    return self.gathered_rgb[slot.value], self.gathered_world_rgb[slot.value]
 
   def reset_host(self, outputs, stream=None) -> None:
     s = self._host_struct(outputs)

@@ -92,3 +92,55 @@ def test_exchange_two_gpus_one_process(territory_blob):
     want = full.timestep_packed.cpu()
     for e in ranks:
       assert torch.equal(e.gathered_timestep().cpu(), want), t
+
+
+def test_gather_obs_world_of_one(commons_blob):
+  # The renderer's extra (peer) stores with the only peer being this rank: the stacked buffer tracks rgb / world_rgb.
+  import torch
+  from meltingpot_b200 import engine
+  B = 200   # balanced rounds + cooperative tail both exercised (148 CTAs x 4 teams > 200: tail only; see next test for rounds)
+  for B in (200, 1300):
+    eng = engine.Engine(commons_blob, B, device=0, seed=9)
+    ptr, _ = eng.gather_obs_create(0, 1)
+    eng.gather_obs_connect([ptr])
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    eng.reset()
+    for t in range(6):
+      eng.gather_obs_wait()
+      torch.cuda.synchronize()
+      rgb, world = eng.gathered_observations()
+      assert torch.equal(rgb, eng.rgb) and torch.equal(world, eng.world_rgb), (B, t)
+      eng.step(torch.randint(0, eng.num_actions, (B, eng.num_players), generator=gen, device='cuda', dtype=torch.int32))
+    eng.gather_obs_enable(False)
+    before = eng.gathered_observations()[0].clone()
+    eng.step(torch.randint(0, eng.num_actions, (B, eng.num_players), generator=gen, device='cuda', dtype=torch.int32))
+    torch.cuda.synchronize()
+    assert torch.equal(eng.gathered_observations()[0], before)  # switched off: nothing delivered
+    eng.close()
+
+
+def test_gather_obs_two_gpus_one_process(clean_up_blob):
+  import torch
+  from meltingpot_b200 import engine
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs 2 GPUs')
+  B = 300
+  ranks = [engine.Engine(clean_up_blob, B, device=r, seed=3, env_index_base=r * B) for r in range(2)]
+  ptrs = [e.gather_obs_create(r, 2)[0] for r, e in enumerate(ranks)]
+  engine.enable_peer_access(0, 1); engine.enable_peer_access(1, 0)
+  for e in ranks:
+    e.gather_obs_connect(ptrs)
+  for e in ranks:
+    e.reset()
+  gen = torch.Generator().manual_seed(1)
+  for t in range(8):
+    for e in ranks:
+      e.gather_obs_wait()
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    want_rgb = torch.cat([e.rgb.cpu() for e in ranks]); want_world = torch.cat([e.world_rgb.cpu() for e in ranks])
+    for e in ranks:
+      rgb, world = e.gathered_observations()
+      assert torch.equal(rgb.cpu(), want_rgb) and torch.equal(world.cpu(), want_world), t
+    a = torch.randint(0, 9, (2 * B, 7), generator=gen, dtype=torch.int32)
+    for r, e in enumerate(ranks):
+      e.step(a[r * B:(r + 1) * B].contiguous().cuda(r))
