@@ -157,10 +157,12 @@ int mp_wait(mp_handle h, int slot);
 
 /* Stacked timestep across GPUs (the path's only exchange). Envs shard over ranks with no
  * data-path collective; what every rank needs back is ONE stacked [world * B] tensor of reward / discount / step type.
- * Instead of a collective kernel per step, every rank's state-transition kernel writes its rows straight into every
- * rank's `gathered` buffer through NVLink peer mappings (P + 2 remote stores per env and rank) and the last warp of
- * the launch raises a per-rank flag; consumers enqueue mp_exchange_wait (a one-warp kernel that fits beside the
- * persistent renderer) before reading mp_buffers.gathered.
+ * Instead of a collective kernel per step, the kernel that follows a state transition in the stream (the renderer,
+ * in its prologue; a small delivery kernel when no render follows) writes this rank's rows straight into every
+ * rank's `gathered` buffer through NVLink peer mappings (P + 2 remote stores per env and rank, hidden behind the
+ * rendering), with no fence on any hot kernel. mp_exchange_wait is the collective point: every rank enqueues it after
+ * its step; its one-warp kernel (which fits beside the persistent renderer) first tells the other ranks that this
+ * rank's rows are complete -- true by the kernel boundary -- and then waits for theirs. Read mp_buffers.gathered after it.
  *   mp_exchange_create   allocates this rank's exchange block: 256 bytes of per-rank flags followed by `gathered`
  *                        (one allocation, so one IPC handle shares it); returns its device pointer and size;
  *   mp_ipc_export/open   turn a device pointer into a 64-byte CUDA IPC handle + offset inside the driver allocation
@@ -170,7 +172,8 @@ int mp_wait(mp_handle h, int slot);
  *                        pointer mp_exchange_create returned); from then on every mp_step / mp_step_state /
  *                        mp_reset publishes. All ranks must issue the same sequence of steps and resets (the slot
  *                        is the parity of the launch sequence number);
- *   mp_exchange_wait     enqueues on `stream` the wait for every rank's flag of the most recent step;
+ *   mp_exchange_wait     enqueues on `stream` (ordered after the step's kernels) the publish-and-wait of the most recent step;
+ *                        every rank must call it once per step;
  *   mp_exchange_slot     which half of `gathered` the most recent step was written to (and its sequence number). */
 int mp_exchange_create(mp_handle h, int rank, int world, void** block, uint64_t* block_bytes);
 int mp_ipc_export(const void* device_ptr, void* handle64, uint64_t* offset);

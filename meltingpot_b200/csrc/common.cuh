@@ -139,7 +139,7 @@ struct State {
   unsigned long long x_step;               // sequence number of this launch; slot = x_step & 1
   double* x_gathered[MP_MAX_PEERS];
   unsigned long long* x_flags[MP_MAX_PEERS];
-  int x_raise;                             // render launches only: 1 = raise this step's flags in the prologue
+  int x_raise;                             // render launches only: 1 = deliver this step's rows (exchange_push / exchange_finish)
   // Stacked observations across GPUs (mp_gather_obs_*): when g_world > 0 the renderer stores every strip not only to
   // this rank's rgb / world_rgb but also, straight from its staging buffer (TMA bulk stores over NVLink peer mappings),
   // into this rank's slab of EVERY rank's stacked buffer. g_rgb / g_wrgb already point at (slot, x_rank's slab).
@@ -214,57 +214,64 @@ __device__ __forceinline__ bool wrap_or_reject(const Tables& T, int& x, int& y) 
   return x >= 0 && x < T.W && y >= 0 && y < T.H;
 }
 
-// Called by every env warp at the end of a state-transition launch (envs a masked reset left untouched publish too, so
-// that the slot of this step is complete). Lane i < P + 2 forwards element i of the env's packed timestep row
-// (reward[0..P), discount, step type) to every rank's gathered buffer with plain stores through the peer mapping: the
-// "all-gather" is P + 2 remote stores per env and rank, issued by the kernel that produced the values, with no
-// collective kernel. Nothing here fences: a system-scope fence per warp (or CTA) costs the launch ~15 us (measured).
-// The kernel boundary already orders these stores, so the flag that tells the other ranks "step s of rank r is
-// complete" is raised by ONE thread of the kernel that follows in the stream (exchange_raise: the renderer's
-// prologue after griddepcontrol.wait, or k_exchange_raise when no render follows).
-// Issued at the top of the launch so that the flow-control read below is off the warp's critical path.
-__device__ __forceinline__ unsigned long long exchange_peek(const State& S, int lane) {
-  if (S.x_world == 0 || lane >= S.x_world) return ~0ull;
-  return *(const volatile unsigned long long*)(S.x_flags[S.x_rank] + lane);
-}
-__device__ __forceinline__ void exchange_publish(const Tables& T, const State& S, int b, int lane, unsigned long long seen) {
+// Delivery of this rank's packed timestep rows (reward[0..P), discount, step type per env) into every rank's gathered
+// buffer: plain stores through the NVLink peer mappings, P + 2 per env and rank -- the "all-gather" of the stacked
+// timestep without a collective kernel. It runs in the kernel that FOLLOWS the state transition (the renderer's
+// prologue, or k_exchange_push when no render follows): the rows are complete there (kernel boundary), the remote
+// round trips hide behind ~200 us of rendering instead of sitting in the tail of the latency-bound transition kernel,
+// and no warp of the transition pays a system-scope fence (measured: 15 us per step when every warp fenced, 6 us
+// with the stores alone in the transition kernel). Called by every thread of every CTA of the delivering grid.
+__device__ __forceinline__ void exchange_push(const Tables& T, const State& S) {
   if (S.x_world == 0) return;
-  __syncwarp();
-  // Flow control: slot (x_step & 1) still holds step x_step - 2 on every rank. A rank has finished with it (its
-  // consumers are stream-ordered before its next launch) once it has published step x_step - 1, so wait for that.
-  // The slowest rank never waits on a faster one, hence no cycle; in steady state the flags were raised a whole
-  // render ago and this is one local read.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (int)blockDim.x >> 5;
+  // Two flag rows per rank: done[r] (flags[0..8), raised by rank r's k_exchange_wait: "my rows of step s are complete here")
+  // and begun[r] (flags[8..16), raised right here: "rank r has started delivering step s"). Flow control: slot
+  // (x_step & 1) still holds step x_step - 2 on every rank, and a rank's consumers of that step are stream-ordered
+  // before its next state transition, so the slot is free once the rank has BEGUN step x_step - 1. That is a whole
+  // render ago in steady state, so ranks are not lock-stepped; the slowest rank never waits on a faster one (no cycle).
+  if (blockIdx.x == 0 && threadIdx.x < S.x_world)
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(S.x_flags[threadIdx.x] + MP_MAX_PEERS + S.x_rank), "l"(S.x_step) : "memory");
   if (lane < S.x_world && S.x_step > 1ull) {
-    const volatile unsigned long long* f = S.x_flags[S.x_rank] + lane;
-    while (seen + 1ull < S.x_step) { __nanosleep(100); seen = *f; }
+    const volatile unsigned long long* f = S.x_flags[S.x_rank] + MP_MAX_PEERS + lane;
+    while (*f + 1ull < S.x_step) __nanosleep(100);
   }
   __syncwarp();
   const int n = T.P + 2;
-  if (lane < n) {
-    const double v = S.packed[(size_t)b * n + lane];
-    const size_t off = ((size_t)(S.x_step & 1ull) * S.x_world * S.B + (size_t)S.x_rank * S.B + b) * n + lane;
-    for (int r = 0; r < S.x_world; ++r) S.x_gathered[r][off] = v;
+  const size_t base = ((size_t)(S.x_step & 1ull) * S.x_world + (size_t)S.x_rank) * S.B;
+  for (int b = (int)blockIdx.x + warp * (int)gridDim.x; b < S.B; b += n_warps * (int)gridDim.x) {
+    if (lane < n) {
+      const double v = S.packed[(size_t)b * n + lane];
+      for (int r = 0; r < S.x_world; ++r) S.x_gathered[r][(base + b) * n + lane] = v;
+    }
   }
 }
 
-// By one thread, after the state-transition kernel of step x_step has completed (kernel boundary: its stores, the
-// remote ones included, have been performed before a dependent kernel runs): flags[x_rank] = x_step on every rank.
-// A plain system-scope store is enough here and a release (= another system fence, ~5 us that would hold up the
-// renderer team this thread belongs to) is not needed: the data is already in place.
-__device__ __forceinline__ void exchange_raise(const State& S) {
-  for (int r = 0; r < S.x_world; ++r) {
-    unsigned long long* f = S.x_flags[r] + S.x_rank;
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(S.x_step) : "memory");
-  }
-}
-__global__ void __launch_bounds__(32) k_exchange_raise(State S) {
+// Delivery when no render follows the state transition (mp_step_state on its own, or rendering switched off).
+__global__ void __launch_bounds__(256) k_exchange_push(Tables T, State S) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (threadIdx.x == 0) exchange_raise(S);
+  exchange_push(T, S);
 }
 
-// One warp: lane r < world waits until rank r has published step `step` into this rank's gathered buffer. Small
-// enough (32 threads, no shared memory) to be resident next to a persistent k_render CTA.
-__global__ void __launch_bounds__(32) k_exchange_wait(const unsigned long long* flags, int world, unsigned long long step) {
+// The consumer side, enqueued by EVERY rank after its step (mp_exchange_wait; stream-ordered after the kernel that
+// delivered, i.e. the renderer): one warp. Lane r first tells rank r "my rows of step `step` are complete in your
+// buffer" -- true without any fence, because the delivering kernel has completed before this one started (kernel
+// boundary) -- and then waits until rank r has said the same here. Collective in the usual sense: a rank's rows become
+// visible to the others when it calls this. Small enough to sit beside a persistent k_render CTA.
+__global__ void __launch_bounds__(32) k_exchange_wait(State S, unsigned long long step) {
+  const int lane = threadIdx.x;
+  if (lane < S.x_world) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(S.x_flags[lane] + S.x_rank), "l"(step) : "memory");
+    const unsigned long long* mine = S.x_flags[S.x_rank] + lane;
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v < step) __nanosleep(200);
+    } while (v < step);
+  }
+}
+
+// One warp: lane r < world waits until local flags[r] has reached `step`.
+__global__ void __launch_bounds__(32) k_flag_wait(const unsigned long long* flags, int world, unsigned long long step) {
   const int lane = threadIdx.x;
   if (lane < world) {
     unsigned long long v;

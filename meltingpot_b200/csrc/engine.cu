@@ -701,7 +701,7 @@ int build_plan(mp_engine* E) {
 
 int raise_flags(mp_engine* E, cudaStream_t st) {
   E->x_pending_raise = false;
-  k_exchange_raise<<<1, 32, 0, st>>>(E->S);
+  k_exchange_push<<<std::min(E->sm_count, (E->B + 7) / 8), 256, 0, st>>>(E->T, E->S);
   ++E->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;
@@ -1192,7 +1192,7 @@ int mp_gather_obs_enable(mp_handle h, int on) {
 int mp_gather_obs_wait(mp_handle h, void* stream) {
   if (!h || !h->g_block) return fail(MP_E_INVALID, "mp_gather_obs_wait: not created");
   DeviceGuard guard(h->device);
-  k_exchange_wait<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(h->g_block), h->g_world, h->g_seq);
+  k_flag_wait<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(h->g_block), h->g_world, h->g_seq);
   ++h->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;
@@ -1209,7 +1209,7 @@ int mp_exchange_wait(mp_handle h, void* stream) {
   if (!h) return fail(MP_E_INVALID, "null handle");
   if (!h->S.x_world) return fail(MP_E_INVALID, "mp_exchange_wait: exchange not connected");
   DeviceGuard guard(h->device);
-  k_exchange_wait<<<1, 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(h->x_block), h->S.x_world, h->x_seq);
+  k_exchange_wait<<<1, 32, 0, (cudaStream_t)stream>>>(h->S, h->x_seq);
   ++h->launches;
   CUDA_TRY(cudaGetLastError());
   return MP_OK;

@@ -292,7 +292,6 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
   // Everything above reads only static tables: with a programmatic dependent launch it overlaps the tail of the
   // state-transition kernel. The env state (grid, avatars) may be read only after this point.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (S.x_raise && blockIdx.x == 0 && tid == 32) exchange_raise(S);  // the step's rows are complete on every rank: tell them
   if (GATHER && tid == 64 && S.g_step > 1ull) {
     // flow control of the stacked buffers: slot (g_step & 1) holds render g_step - 2; a rank is done with it once it has
     // delivered render g_step - 1 (its consumers are stream-ordered before that launch)
@@ -435,6 +434,9 @@ __global__ void __launch_bounds__(RENDER_MAX_THREADS, 1) k_render(Tables T, Stat
         }
       }
     }
+    // this rank's timestep rows -> every rank's gathered buffer: by each warp once it has run out of strips of its first
+    // env, so the loads and the remote stores overlap the other warps' drawing instead of delaying the kernel's start
+    if (S.x_raise && it == 0) exchange_push(T, S);
     group_sync(bar_id, gthreads);  // every warp is done with s_rec / s_view
     if (gtid == 0) *next_ctr = 0;
     // (the reset is ordered before the next env's item loop by the group barrier after its cell pass)

@@ -444,7 +444,6 @@ __global__ void __launch_bounds__(128, 8) k_step_clean_up(Tables T, State S, con
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int b = blockIdx.x * 4 + warp;
   if (b >= S.B) return;
-  const unsigned long long x_seen = exchange_peek(S, lane);
   WarpScratch sc = carve_scratch(T, smem + warp * warp_scratch_bytes(T));
   if (!(mode == 1 && !(mask == nullptr || mask[b]))) {
     event_begin(lane);
@@ -452,5 +451,4 @@ __global__ void __launch_bounds__(128, 8) k_step_clean_up(Tables T, State S, con
     else clean_up_step(T, S, b, lane, actions, sc);
     event_end(S, b, lane);
   }
-  exchange_publish(T, S, b, lane, x_seen);
 }

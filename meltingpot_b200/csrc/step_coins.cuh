@@ -233,7 +233,6 @@ __global__ void __launch_bounds__(128, 8) k_step_coins(Tables T, State S, const 
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int b = blockIdx.x * 4 + warp;
   if (b >= S.B) return;
-  const unsigned long long x_seen = exchange_peek(S, lane);
   WarpScratch sc = carve_scratch(T, smem + warp * warp_scratch_bytes(T));
   if (!(mode == 1 && !(mask == nullptr || mask[b]))) {
     event_begin(lane);
@@ -241,5 +240,4 @@ __global__ void __launch_bounds__(128, 8) k_step_coins(Tables T, State S, const 
     else coins_step(T, S, b, lane, actions, sc);
     event_end(S, b, lane);
   }
-  exchange_publish(T, S, b, lane, x_seen);
 }

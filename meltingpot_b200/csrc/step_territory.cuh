@@ -428,7 +428,6 @@ __global__ void __launch_bounds__(128, 8) k_step_territory(Tables T, State S, co
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int b = blockIdx.x * 4 + warp;
   if (b >= S.B) return;
-  const unsigned long long x_seen = exchange_peek(S, lane);
   TerritoryScratch sc = carve_territory(T, smem + warp * territory_scratch_bytes(T));
   int32_t* env = S.env + (size_t)b * ENV_COLS;
   const uint64_t key = S.seed + (uint64_t)b;
@@ -448,5 +447,4 @@ __global__ void __launch_bounds__(128, 8) k_step_territory(Tables T, State S, co
     }
     event_end(S, b, lane);
   }
-  exchange_publish(T, S, b, lane, x_seen);
 }
