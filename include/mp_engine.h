@@ -222,6 +222,15 @@ int mp_debug_render_plan(mp_handle h, int32_t out[8]);
  * bit 1 remapped per viewer. Either array may be NULL (call once for n_total, then again). */
 int mp_debug_render_tables(mp_handle h, int32_t* n_total, uint8_t* pair, uint8_t* flags);
 
+/* Debug observations of the current timestep, written into caller-owned DEVICE buffers (any
+ * may be NULL): position i32 [B][P][2] = (x, y) of each avatar, 0-based ("{i}.POSITION", LocationObserver,
+ * component_library.lua:806-855; an avatar that is off the map keeps its last cell), orientation i32 [B][P] = 0 N, 1 E,
+ * 2 S, 3 W ("{i}.ORIENTATION"), layer i32 [B][P][view_h][view_w][L] = the avatar's UNROTATED view window as per-layer
+ * sprite ids + 1, 0 = empty, -1 = outside a BOUNDED map ("{i}.LAYER", avatar_library.lua:247-257 with orientation 'N'),
+ * zap_matrix i32 [B][P][P] = how often player row zapped player column this step (from the step's 'zap' events, as
+ * clean_up.py:751-784's metric does). Off by default in the reference's configs and off the hot path here. */
+int mp_debug_observations(mp_handle h, int32_t* position, int32_t* orientation, int32_t* layer, int32_t* zap_matrix, void* stream);
+
 /* Diagnostic (needs no device): the renderer's lane -> cell dealing for a strip of `n_rows` pixel rows x `n_cells` cells
  * at a row pitch of `pitch_slots` 8-byte slots, `iters` turns per lane: out[lane] holds 6 bits per turn (63 = idle).
  * Lane l draws pixel row l % n_rows. scattered = 0: the default dealing (whole cells per lane group and turn, cell order

@@ -699,6 +699,38 @@ int build_plan(mp_engine* E) {
   return MP_OK;
 }
 
+// Debug observations: {i}.POSITION / {i}.ORIENTATION (LocationObserver, component_library.lua:806-855),
+// {i}.LAYER (the unrotated view window as per-layer sprite ids, avatar_library.lua:247-257) and the per-step zap matrix
+// (who zapped whom, from the step's events; clean_up.py:751-784 builds the same from the 'zap' events).
+__global__ void k_debug_obs(Tables T, State S, int32_t* position, int32_t* orientation, int32_t* layer, int32_t* zap, int view_w, int view_h) {
+  const int b = blockIdx.x, P = T.P;
+  const int32_t* av = S.avatar + (size_t)b * P * 4;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    if (position) { position[((size_t)b * P + p) * 2] = av[p * 4 + AV_X]; position[((size_t)b * P + p) * 2 + 1] = av[p * 4 + AV_Y]; }
+    if (orientation) orientation[(size_t)b * P + p] = av[p * 4 + AV_ORIENT];
+  }
+  if (layer) {
+    const int per_player = view_h * view_w * T.L;
+    const uint16_t* grid = S.grid + (size_t)b * T.L * T.cells_pad;
+    for (int i = threadIdx.x; i < P * per_player; i += blockDim.x) {
+      const int p = i / per_player, r = i - p * per_player, l = r % T.L, c = r / T.L, vx = c % view_w, vy = c / view_w;
+      int x = av[p * 4 + AV_X] - T.view_l + vx, y = av[p * 4 + AV_Y] - T.view_f + vy;  // orientation 'N': window not rotated
+      int32_t v = -1;  // outside a BOUNDED map (policy A.21)
+      if (wrap_or_reject(T, x, y)) { const uint16_t g = grid[(size_t)l * T.cells_pad + y * T.W + x]; v = g ? ((g - 1) >> 2) + 1 : 0; }
+      layer[(size_t)b * P * per_player + i] = v;
+    }
+  }
+  if (zap) {
+    for (int i = threadIdx.x; i < P * P; i += blockDim.x) zap[(size_t)b * P * P + i] = 0;
+    __syncthreads();
+    const int n = min(S.n_events[b], S.max_events);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int32_t* e = S.events + ((size_t)b * S.max_events + i) * 3;
+      if (e[0] == EV_ZAP && e[1] >= 1 && e[1] <= P && e[2] >= 1 && e[2] <= P) atomicAdd(&zap[(size_t)b * P * P + (e[1] - 1) * P + (e[2] - 1)], 1);
+    }
+  }
+}
+
 int raise_flags(mp_engine* E, cudaStream_t st) {
   E->x_pending_raise = false;
   k_exchange_push<<<std::min(E->sm_count, (E->B + 7) / 8), 256, 0, st>>>(E->T, E->S);
@@ -1294,6 +1326,15 @@ int mp_debug_render_tables(mp_handle h, int32_t* n_total, uint8_t* pair, uint8_t
   if (n_total) *n_total = h->n_total;
   if (pair) memcpy(pair, h->host_pair.data(), h->host_pair.size());
   if (flags) memcpy(flags, h->host_sflags.data(), h->host_sflags.size());
+  return MP_OK;
+}
+
+int mp_debug_observations(mp_handle h, int32_t* position, int32_t* orientation, int32_t* layer, int32_t* zap_matrix, void* stream) {
+  if (!h) return fail(MP_E_INVALID, "null handle");
+  DeviceGuard guard(h->device);
+  k_debug_obs<<<h->B, 128, 0, (cudaStream_t)stream>>>(h->T, h->S, position, orientation, layer, zap_matrix, h->R.view_w, h->R.view_h);
+  ++h->launches;
+  CUDA_TRY(cudaGetLastError());
   return MP_OK;
 }
 

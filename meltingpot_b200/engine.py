@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     'mp_step_state', 'mp_render', 'mp_get_buffers', 'mp_step_host',
     'mp_reset_host', 'mp_launch_count', 'mp_algorithmic_bytes', 'mp_debug_render_tables', 'mp_debug_render_plan', 'mp_state_size', 'mp_state_save', 'mp_state_load',
     'mp_step_host_async', 'mp_wait', 'mp_exchange_create', 'mp_ipc_export', 'mp_ipc_open', 'mp_enable_peer_access',
-    'mp_exchange_connect', 'mp_exchange_wait', 'mp_exchange_slot', 'mp_debug_lane_map',
+    'mp_exchange_connect', 'mp_exchange_wait', 'mp_exchange_slot', 'mp_debug_lane_map', 'mp_debug_observations',
     'mp_gather_obs_create', 'mp_gather_obs_connect', 'mp_gather_obs_enable', 'mp_gather_obs_wait', 'mp_gather_obs_slot',
     'mp_last_error', 'mp_version',
 )
@@ -108,6 +108,7 @@ def load_library() -> ctypes.CDLL:
   lib.mp_gather_obs_enable.argtypes = [vp, ctypes.c_int]
   lib.mp_gather_obs_wait.argtypes = [vp, vp]
   lib.mp_gather_obs_slot.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint64)]
+  lib.mp_debug_observations.argtypes = [vp] * 6
   lib.mp_debug_lane_map.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_uint32)]
   lib.mp_last_error.restype = ctypes.c_char_p
   lib.mp_version.restype = ctypes.c_char_p
@@ -388,6 +389,24 @@ class Engine:
     slot = ctypes.c_int(0)
     _check(self._lib.mp_gather_obs_slot(self._h, ctypes.byref(slot), None))
     return self.gathered_rgb[slot.value], self.gathered_world_rgb[slot.value]
+
+  def debug_observations(self, layer: bool = True, zap_matrix: bool = True, stream=None):
+    """{'POSITION' [B,P,2], 'ORIENTATION' [B,P], 'LAYER' [B,P,vh,vw,L], 'ZAP_MATRIX' [B,P,P]} int32 CUDA tensors of the
+    current timestep (mp_debug_observations)."""
+    torch = self._torch
+    dev = torch.device('cuda', self.device)
+    b = self.buffers
+    B, P = self.num_envs, self.num_players
+    out = {'POSITION': torch.empty((B, P, 2), dtype=torch.int32, device=dev),
+           'ORIENTATION': torch.empty((B, P), dtype=torch.int32, device=dev)}
+    if layer:
+      out['LAYER'] = torch.empty((B, P, b.rgb_h // 8, b.rgb_w // 8, b.grid_layers), dtype=torch.int32, device=dev)
+    if zap_matrix:
+      out['ZAP_MATRIX'] = torch.empty((B, P, P), dtype=torch.int32, device=dev)
+    ptr = lambda k: ctypes.c_void_p(out[k].data_ptr()) if k in out else None
+    _check(self._lib.mp_debug_observations(self._h, ptr('POSITION'), ptr('ORIENTATION'), ptr('LAYER'), ptr('ZAP_MATRIX'),
+                                           self._stream(stream)))
+    return out
 
   def reset_host(self, outputs, stream=None) -> None:
     s = self._host_struct(outputs)

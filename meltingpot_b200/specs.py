@@ -25,6 +25,8 @@ REWARD = dm_env.specs.Array(shape=(), dtype=np.float64, name='reward')
 OBSERVATION = {
     'READY_TO_SHOOT': dm_env.specs.Array(shape=(), dtype=np.float64, name='READY_TO_SHOOT'),
     'RGB': dm_env.specs.Array(shape=(88, 88, 3), dtype=np.uint8, name='RGB'),
+    'POSITION': dm_env.specs.Array(shape=(2,), dtype=np.int32, name='POSITION'),  # specs.py:39-44 of the reference
+    'ORIENTATION': dm_env.specs.Array(shape=(), dtype=np.int32, name='ORIENTATION'),
 }
 _ACTION = dm_env.specs.DiscreteArray(num_values=1, dtype=np.int64, name='action')
 

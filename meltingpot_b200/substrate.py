@@ -174,6 +174,11 @@ class BatchedSubstrate:
     self._engine.step(actions.contiguous())
     return self._timestep()
 
+  def debug_observations(self, layer: bool = True, zap_matrix: bool = True):
+    """The reference's debug observations of the current timestep as int32 tensors: 'POSITION' [B, P, 2],
+    'ORIENTATION' [B, P] (specs.py:39-44), 'LAYER' [B, P, view_h, view_w, layers], 'ZAP_MATRIX' [B, P, P]."""
+    return self._engine.debug_observations(layer=layer, zap_matrix=zap_matrix)
+
   def events(self):
     """(event_count int32 [B], events int32 [B, max_events, 3]) of the last step; rows are (type, a, b), unordered."""
     return self._engine.event_count, self._engine.events

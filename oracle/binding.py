@@ -49,6 +49,7 @@ def lib() -> ctypes.CDLL:
     L.oracle_get_avatars.argtypes = [vp, i32p]
     L.oracle_get_grid.argtypes = [vp, ctypes.POINTER(ctypes.c_uint16)]
     L.oracle_get_events.argtypes = [vp, i32p, ctypes.c_int]
+    L.oracle_layer_view.argtypes = [vp, ctypes.c_int, i32p]
     L.oracle_get_object_state.argtypes = [vp, ctypes.c_int]
     L.oracle_get_counters.argtypes = [vp, i32p]
     L.oracle_render_player.argtypes = [vp, ctypes.c_int, u8p]
@@ -161,6 +162,13 @@ class OracleEnv:
     out = np.zeros((256, 3), np.int32)
     n = lib().oracle_get_events(self._h, _ptr(out, ctypes.c_int32), 256)
     return [(EVENT_NAMES[int(t)], int(a), int(b)) for t, a, b in out[:min(n, 256)]]
+
+  def layer_view(self):
+    vh, vw = self.rgb_shape[0] // self.S, self.rgb_shape[1] // self.S
+    out = np.zeros((self.P, vh, vw, self.L), np.int32)
+    for p in range(self.P):
+      lib().oracle_layer_view(self._h, p, _ptr(out[p], ctypes.c_int32))
+    return out
 
   def object_state(self, oid: int) -> int:
     return lib().oracle_get_object_state(self._h, oid)

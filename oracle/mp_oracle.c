@@ -1111,6 +1111,7 @@ void oracle_get_avatars(const OrEnv* e, int32_t* out) {
   for (int p = 0; p < e->P; ++p) { const Obj* o = &e->obj[e->avatar_obj[p]]; out[p * 4] = o->x; out[p * 4 + 1] = o->y; out[p * 4 + 2] = o->orient; out[p * 4 + 3] = o->layer >= 0; }
 }
 /* Sprite grid in the engine's encoding: out[L][cells] uint16 (beams merged in). */
+void oracle_get_grid(const OrEnv* e, uint16_t* out);
 void oracle_get_grid(const OrEnv* e, uint16_t* out) {
   int cells = e->W * e->H;
   for (int l = 0; l < e->L; ++l) for (int c = 0; c < cells; ++c) {
@@ -1119,6 +1120,24 @@ void oracle_get_grid(const OrEnv* e, uint16_t* out) {
     if (e->beam[l * cells + c]) v = e->beam[l * cells + c];
     out[l * cells + c] = v;
   }
+}
+/* {p}.LAYER (avatar_library.lua:247-257: playerLayerView:observation{grid, piece, orientation = 'N'}): the avatar's view
+ * window, NOT rotated, as sprite id + 1 per layer; 0 empty, -1 outside a BOUNDED map (policy A.21). out[view_h][view_w][L]. */
+void oracle_layer_view(const OrEnv* e, int p, int32_t* out) {
+  const Obj* a = &e->obj[e->avatar_obj[p]];
+  const int vw = e->view_l + e->view_r + 1, vh = e->view_f + e->view_b + 1, cells = e->W * e->H;
+  uint16_t* g = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)e->L * cells);
+  oracle_get_grid(e, g);
+  for (int vy = 0; vy < vh; ++vy) for (int vx = 0; vx < vw; ++vx) {
+    int x = a->x - e->view_l + vx, y = a->y - e->view_f + vy;
+    const int inside = wrap_or_reject(e, &x, &y);
+    for (int l = 0; l < e->L; ++l) {
+      int32_t v = -1;
+      if (inside) { const uint16_t q = g[(size_t)l * cells + y * e->W + x]; v = q ? ((q - 1) >> 2) + 1 : 0; }
+      out[((size_t)vy * vw + vx) * e->L + l] = v;
+    }
+  }
+  free(g);
 }
 int oracle_get_events(const OrEnv* e, int32_t* out, int max_events) {
   int n = e->evn < max_events ? e->evn : max_events;
