@@ -274,30 +274,73 @@ def _map_rows(ascii_map: str) -> List[str]:
   return rows
 
 
-def _expand_prefab(spec, prefabs, out, x, y, rng):
+def _flatten_option(spec) -> List[str]:
+  """Prefab names of one option of a 'choice' ('all' lists are expanded; a nested 'choice' is refused)."""
+  if isinstance(spec, Mapping):
+    if spec['type'] != 'all':
+      raise NotImplementedError("a 'choice' prefab nested inside a 'choice'")
+    out: List[str] = []
+    for p in spec['list']:
+      out += _flatten_option(p)
+    return out
+  return [spec]
+
+
+def _expand_prefab(spec, prefabs, out, x, y, rng, choices=None):
   """prefab_utils.lua:44-72 (_createPrefabsFromSpec): a name, or {'type': 'all' | 'choice', 'list': [...]}.
 
-  The reference draws a 'choice' with the env's own random stream when the env is built, so every
-  env instance gets its own layout. Here the draw happens once per compiled blob with `rng`
-  (policy A.20: all env instances of a batch share the layout); without a build seed it is refused.
+  The reference draws a 'choice' with the env's own random stream when the env is built -- i.e. for every env
+  instance and, because the ResetWrapper rebuilds the env, for every episode. Without a build seed the draw is left
+  to the engine: the prefabs common to all options are emitted as usual, the others become CONDITIONAL objects
+  tagged (choice group, bit mask of the tickets 0..n_options-1 on which they exist); every env draws one ticket per
+  group at each episode start (kernels and oracle alike). `out` entries are (prefab, x, y, condition or None).
+  With a build seed (`rng`) one draw is fixed at compile time for all envs (the old behaviour, policy A.20).
   """
   if isinstance(spec, Mapping):
     if spec['type'] == 'all':
       for p in spec['list']:
-        _expand_prefab(p, prefabs, out, x, y, rng)
+        _expand_prefab(p, prefabs, out, x, y, rng, choices)
     elif spec['type'] == 'choice':
-      if rng is None:
-        raise NotImplementedError(
-            "charPrefabMap type 'choice' (random choice at build time) needs a build_seed: "
-            'the B200 engine draws the layout once per compiled blob')
       options = list(spec['list'])
-      _expand_prefab(options[rng.randrange(len(options))], prefabs, out, x, y, rng)
+      if rng is not None:
+        _expand_prefab(options[rng.randrange(len(options))], prefabs, out, x, y, rng, choices)
+        return
+      if choices is None or len(options) > 31:
+        raise NotImplementedError("charPrefabMap type 'choice' with more than 31 options")
+      flat = [_flatten_option(o) for o in options]
+      common = list(flat[0])
+      for f in flat[1:]:
+        rest = list(f)
+        kept = []
+        for name in common:
+          if name in rest:
+            rest.remove(name)
+            kept.append(name)
+        common = kept
+      for name in common:
+        _expand_prefab(name, prefabs, out, x, y, rng, choices)
+      group = len(choices)
+      choices.append(len(options))
+      extras: Dict[str, int] = {}  # prefab name (with multiplicity index) -> ticket mask
+      for t, f in enumerate(flat):
+        rest = list(f)
+        for name in common:
+          rest.remove(name)
+        seen: Dict[str, int] = {}
+        for name in rest:
+          k = seen.get(name, 0)
+          seen[name] = k + 1
+          extras[(name, k)] = extras.get((name, k), 0) | (1 << t)
+      for (name, _), mask in extras.items():
+        if name not in prefabs:
+          raise KeyError(f"Prefab with name '{name}' not found in prefabs.")
+        out.append((prefabs[name], x, y, (group, mask)))
     else:
       raise NotImplementedError(f"charPrefabMap type {spec['type']!r} is not supported by the B200 engine")
   else:
     if spec not in prefabs:
       raise KeyError(f"Prefab with name '{spec}' not found in prefabs.")
-    out.append((prefabs[spec], x, y))
+    out.append((prefabs[spec], x, y, None))
 
 
 class WorldModel:
@@ -325,15 +368,16 @@ class WorldModel:
     # ---- objects in creation order (base_simulation.lua:102-134) ----------
     objs = []  # (config, x, y)
     if sim.get('scene') is not None:
-      objs.append((sim['scene'], 0, 0))
+      objs.append((sim['scene'], 0, 0, None))
     for go in sim.get('gameObjects', []):
-      objs.append((go, 0, 0))
+      objs.append((go, 0, 0, None))
     cpm = {str(k): v for k, v in sim['charPrefabMap'].items()}
     rng = random.Random(build_seed) if build_seed is not None else None
+    self.choice_options: List[int] = []   # options per 'choice' group (drawn per env and episode by the engine)
     for y, row in enumerate(rows):
       for x, ch in enumerate(row):
         if ch in cpm:
-          _expand_prefab(cpm[ch], sim['prefabs'], objs, x, y, rng)
+          _expand_prefab(cpm[ch], sim['prefabs'], objs, x, y, rng, self.choice_options)
     self.objects_cfg = objs
     self._prefabs = sim.get('prefabs', {})
     self.avatar_roles = set()
@@ -347,7 +391,7 @@ class WorldModel:
         self.hits.append((hit, layer, sprite))
       if insert_layer and layer not in self.layers:
         self.layers.append(layer)
-    for cfg, _, _ in objs:
+    for cfg, _, _, _ in objs:
       for c in cfg['components']:
         kw = c.get('kwargs', {}) or {}
         if c['component'] in _HIT_OF:
@@ -368,7 +412,7 @@ class WorldModel:
     sp = SpriteSet(self.sprite_size)
     sp.add_color('OutOfBounds', (0, 0, 0))
     sp.add_color('OutOfView', (80, 80, 80))
-    for cfg, _, _ in objs:
+    for cfg, _, _, _ in objs:
       for c in cfg['components']:
         kw = c.get('kwargs', {}) or {}
         if c['component'] == 'Appearance':
@@ -389,7 +433,7 @@ class WorldModel:
 
     # ---- groups -------------------------------------------------------------
     self.groups: List[str] = []
-    for cfg, _, _ in objs:
+    for cfg, _, _, _ in objs:
       sm = _first(cfg['components'], 'StateManager')
       for st in sm['kwargs']['stateConfigs']:
         for g in st.get('groups', []) or []:
@@ -411,7 +455,8 @@ class WorldModel:
     self.avatar_objs: List[int] = []
     self.view = None
     self.sprite_maps: Dict[int, Dict[str, str]] = {}
-    for oid, (cfg, x, y) in enumerate(objs):
+    self.obj_choice: List[List[int]] = []
+    for oid, (cfg, x, y, cond) in enumerate(objs):
       comps = cfg['components']
       tr = _first(comps, 'Transform')
       tkw = (tr or {}).get('kwargs', {}) or {}
@@ -430,6 +475,19 @@ class WorldModel:
       sm = _first(comps, 'StateManager')['kwargs']
       init = self.state_names[kid].index(sm['initialState'])
       self.objects.append([kid, int(x), int(y), orient, init])
+      self.obj_choice.append([cond[0], cond[1]] if cond else [-1, 0])
+      if cond:
+        # What may depend on the per-env draw: invisible component-free pieces (spawn points), and territory's resource
+        # bundle (resource + its texture / reward indicator / damage indicator on the same cell, all on one condition),
+        # which the territory kernel and the oracle both treat as "this resource does not exist in this episode".
+        names = {c['component'] for c in comps}
+        states = self.states[self.kinds[kid][0]:self.kinds[kid][0] + self.kinds[kid][1]]
+        inert = names <= {'StateManager', 'Transform', 'Appearance'} and all(st[1] < 0 and st[2] < 0 for st in states)
+        bundle = cfg.get('name') in ('resource', 'resource_texture', 'reward_indicator', 'damage_indicator')
+        if not (inert or (bundle and self.family == 'territory')):
+          raise NotImplementedError(f"'choice' prefab {cfg.get('name')!r} cannot depend on the per-env draw in the B200 engine "
+                                    '(supported: invisible component-free pieces, territory resource bundles); pass a build_seed '
+                                    'to fix one draw at compile time')
       if self.kinds[kid][4]:
         self.avatar_objs.append(oid)
     if len(self.avatar_objs) != self.num_players:
@@ -742,16 +800,20 @@ def _avatar_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
   sections['av_table'] = av
   # Spawn cells per group, in object (piece) order.
   for gi, g in enumerate(model.groups):
-    cells = []
-    for (kid, x, y, orient, st) in model.objects:
+    cells, conds = [], []
+    for oid, (kid, x, y, orient, st) in enumerate(model.objects):
       state = model.states[model.kinds[kid][0] + st]
       if state[3] & (1 << gi) and not model.kinds[kid][4]:
         cells.append(y * model.W + x)
+        conds.append(model.obj_choice[oid])
     if g in ('spawnPoints', 'insideSpawnPoints'):
       sections['spawn_cells_' + str(gi)] = np.array(cells, np.int32)
+      if any(c[0] >= 0 for c in conds):  # members that exist only on some tickets of their 'choice' group
+        sections['spawn_cond_' + str(gi)] = np.array(conds, np.int32).reshape(-1, 2)
       users = int((av[:, 3] == gi).sum())
-      if len(cells) < users:  # (possible when spawn points come from 'choice' prefabs)
-        raise ValueError(f'{users} avatars start in group {g!r} but the map has only {len(cells)} such cells')
+      if sum(1 for c in conds if c[0] < 0) < users:
+        raise ValueError(f'{users} avatars start in group {g!r} but the map guarantees only '
+                         f'{sum(1 for c in conds if c[0] < 0)} such cells')
   # Static beam blockers: bit h set if a BeamBlocker for hit h sits on the cell.
   flags = np.zeros(model.H * model.W, np.uint8)
   for oid, ci in _objects_with(model, 'BeamBlocker'):
@@ -1121,6 +1183,16 @@ def _territory_tables(model: WorldModel, sections: Dict[str, np.ndarray]):
   sections['tr_ip'] = ip
   sections['tr_dp'] = dp
   sections['tr_res'] = np.array([[r[0], r[1], r[4]] for r in res], np.int32)
+  if model.choice_options:  # resources that exist only on some tickets of their 'choice' group (territory__inside_out's A / B cells)
+    cond = np.array([model.obj_choice[r[0]] for r in res], np.int32).reshape(-1, 2)
+    by_cell = {}
+    for oid, (kid, x, y, orient, st) in enumerate(model.objects):
+      if model.obj_choice[oid][0] >= 0 and model.kind_names[kid] in ('resource', 'resource_texture', 'reward_indicator', 'damage_indicator'):
+        by_cell.setdefault(y * model.W + x, set()).add(tuple(model.obj_choice[oid]))
+    for r in res:  # the four pieces of a resource cell come and go together
+      if len(by_cell.get(r[1], {tuple(model.obj_choice[r[0]])})) != 1 or (model.obj_choice[r[0]][0] >= 0) != (r[1] in by_cell):
+        raise NotImplementedError('a resource and its texture / indicators must share one choice condition')
+    sections['tr_res_cond'] = cond
   per_player = np.zeros((P, 4), np.int32)
   ind_kind = model.kind_names.index('reward_indicator')
   for i in range(P):
@@ -1205,6 +1277,9 @@ def compile_settings(settings: Mapping[str, Any],
       'scalar_obs': np.array(scalar_obs, np.int32),
       'init_grid': model.init_grid(),
   }
+  if model.choice_options:
+    sections['choice_groups'] = np.array(model.choice_options, np.int32)
+    sections['obj_choice'] = np.array(model.obj_choice, np.int32).reshape(-1, 2)
   _avatar_tables(model, sections)
   if model.family == 'clean_up':
     _clean_up_tables(model, sections)

@@ -27,7 +27,7 @@ enum { ENV_STEP = 0, ENV_EPISODE = 1, ENV_DONE = 2, ENV_DIRT = 3, ENV_CLEANED = 
 enum { AV_X = 0, AV_Y = 1, AV_ORIENT = 2, AV_ALIVE = 3 };
 enum { TM_ZAP = 0, TM_BEAM2 = 1, TM_FRAME = 2 };
 // RNG streams: must match oracle/mp_oracle.c (the RNG addressing is part of the engine policy).
-enum { RS_SCENE = 0, RS_AVATAR = 1, RS_OBJECT = 2, RS_AVATAR_RESET = 3, RS_OBJECT_RESET = 4 };
+enum { RS_SCENE = 0, RS_AVATAR = 1, RS_OBJECT = 2, RS_AVATAR_RESET = 3, RS_OBJECT_RESET = 4, RS_CHOICE = 5 };
 enum { SCENE_DRAW_DIRT = 0, SCENE_DRAW_EPISODE_END = 1 };
 
 struct BeamGeom {  // one beam footprint, cells in visiting order (policy A.8)
@@ -76,6 +76,11 @@ struct Tables {
   const int32_t* tr_res;       // [nR][3] obj id, cell, initial state
   const int16_t* res_of_cell;  // [cells_pad] resource index or -1
   const uint8_t* wall;         // [cells_pad] 1 where an AllBeamBlocker piece stands
+  // 'choice' prefabs drawn per env and episode (prefab_utils.lua:63-65): ticket of group g = pick(philox(0, episode, g, RS_CHOICE).x, choice_n[g])
+  int n_choice;
+  const int32_t* choice_n;     // [n_choice] options per group
+  const int32_t* spawn_cond;   // [n_spawn][2] (group or -1, ticket mask) of each spawn candidate, or null
+  const int32_t* tr_res_cond;  // [nR][2] same for each resource, or null
   const int32_t* ch_nbr;       // [nA][16] apples inside the regrowth disc (excluding self), -1 padded
   // device tables
   const uint16_t* init_grid;   // [L][cells_pad]
@@ -197,6 +202,13 @@ __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
 __device__ __forceinline__ uint32_t pick(uint32_t w, uint32_t n) { return __umulhi(w, n); }
+
+// Does a piece with condition (group, mask) exist in this env's current episode?
+__device__ __forceinline__ bool choice_present(const Tables& T, int group, uint32_t mask, int episode, uint32_t k0, uint32_t k1) {
+  if (group < 0) return true;
+  const uint4 w = philox4x32_10(0u, (uint32_t)episode, (uint32_t)group, RS_CHOICE, k0, k1);
+  return (mask >> pick(w.x, (uint32_t)T.choice_n[group])) & 1u;
+}
 
 __device__ __forceinline__ int dir_dx(int d) { return (d == 1) - (d == 3); }
 __device__ __forceinline__ int dir_dy(int d) { return (d == 2) - (d == 0); }

@@ -464,8 +464,30 @@ int build_tables(mp_engine* E, const void* blob, size_t n) {
     std::vector<uint8_t> wall(T.cells_pad, 0);
     memcpy(wall.data(), tr_wall.data, std::min<size_t>(tr_wall.count, T.cells));
     if ((rc = E->upload(v_res, &T.tr_res)) || (rc = E->upload(res_of, &T.res_of_cell)) || (rc = E->upload(wall, &T.wall))) return rc;
+    Section<int32_t> tr_res_cond;
+    if (get_section(blob, n, "tr_res_cond", MPB_I32, &tr_res_cond)) {
+      if ((int)tr_res_cond.count != T.nR * 2) return fail(MP_E_INVALID, "blob: tr_res_cond has %zu values for %d resources", tr_res_cond.count, T.nR);
+      std::vector<int32_t> v(tr_res_cond.data, tr_res_cond.data + tr_res_cond.count);
+      if ((rc = E->upload(v, &T.tr_res_cond))) return rc;
+    }
   }
 #undef NEED
+  {  // 'choice' prefabs left to the engine (drawn per env and episode)
+    Section<int32_t> choice_groups, obj_choice, spawn_cond;
+    if (get_section(blob, n, "choice_groups", MPB_I32, &choice_groups)) {
+      if (E->family != MPB_FAMILY_TERRITORY) return fail(MP_E_UNSUPPORTED, "per-env 'choice' prefabs are implemented for the territory family only (compile with a build_seed)");
+      T.n_choice = (int)choice_groups.count;
+      for (size_t g = 0; g < choice_groups.count; ++g) if (choice_groups.data[g] < 1 || choice_groups.data[g] > 31) return fail(MP_E_INVALID, "blob: choice group with %d options", choice_groups.data[g]);
+      std::vector<int32_t> v(choice_groups.data, choice_groups.data + choice_groups.count);
+      if ((rc = E->upload(v, &T.choice_n))) return rc;
+      snprintf(name, sizeof name, "spawn_cond_%d", respawn_group);
+      if (get_section(blob, n, name, MPB_I32, &spawn_cond)) {
+        if ((int)spawn_cond.count != T.n_spawn * 2 || T.n_spawn > 64) return fail(MP_E_UNSUPPORTED, "%d conditional spawn candidates (max 64)", T.n_spawn);
+        std::vector<int32_t> c(spawn_cond.data, spawn_cond.data + spawn_cond.count);
+        if ((rc = E->upload(c, &T.spawn_cond))) return rc;
+      }
+    }
+  }
   T.nA_pad = round_up(std::max(T.nA, 1), 16); T.nD_pad = round_up(std::max(std::max(T.nD, T.nA), 1), 16); T.nW_pad = round_up(std::max(T.nW, 1), 16);
 
   // ---- device copies -----------------------------------------------------------------------------

@@ -20,7 +20,7 @@
 #include "step_clean_up.cuh"  // beam_scan
 
 // Resource state codes: 0 unclaimed, 1 destroyed, 2 + i claimed_by_(i+1).
-enum { RF_ACTIVE = 1, RF_NEVER_CLAIMED = 2, RF_DESTROYED = 4 };
+enum { RF_ACTIVE = 1, RF_NEVER_CLAIMED = 2, RF_DESTROYED = 4, RF_ABSENT = 8 /* not drawn into this episode's map ('choice' prefab) */ };
 // fam_u8 sub-arrays (each nR_pad long), fam_u16 sub-arrays.
 enum { RU_STATE = 0, RU_HEALTH = 1, RU_FLAGS = 2, RU_CLAIMER = 3, RU_IND = 4, RU_DMG = 5, RU_TEX = 6, RU_COUNT = 7 };
 enum { RS_FSZ = 0, RS_FRAME = 1, RS_COUNT = 2 };
@@ -85,15 +85,36 @@ __device__ void territory_init(const Tables& T, const State& S, int b, int lane,
     u8[RU_CLAIMER * T.nR_pad + k] = 0xFF;
     u8[RU_IND * T.nR_pad + k] = 0; u8[RU_DMG * T.nR_pad + k] = 0; u8[RU_TEX * T.nR_pad + k] = 0;
     u16[RS_FSZ * T.nR_pad + k] = 0; u16[RS_FRAME * T.nR_pad + k] = 0;
+    if (T.tr_res_cond && !choice_present(T, T.tr_res_cond[k * 2], (uint32_t)T.tr_res_cond[k * 2 + 1], episode, k0, k1)) {
+      // This episode's map has plain floor here: the resource, its texture and its two indicators were not created.
+      // Kept as a destroyed resource that never had a texture: nothing stands on the cell, nothing is drawn, nothing updates.
+      const int cell = T.tr_res[k * 3 + 1];
+      u8[RU_STATE * T.nR_pad + k] = 1; u8[RU_FLAGS * T.nR_pad + k] = RF_DESTROYED | RF_ABSENT; u8[RU_TEX * T.nR_pad + k] = 1;
+      grid[(size_t)T.res_layer * T.cells_pad + cell] = 0; grid[(size_t)T.tex_layer * T.cells_pad + cell] = 0;
+      grid[(size_t)T.ind_layer * T.cells_pad + cell] = 0; grid[(size_t)T.dmg_layer * T.cells_pad + cell] = 0;
+    }
   }
-  // spawn: partial Fisher-Yates over the spawn group (base_simulation.lua:396-445)
+  // spawn: partial Fisher-Yates over the spawn group (base_simulation.lua:396-445); with 'choice' spawn points the
+  // group's members are this episode's draw, kept in piece order
   int16_t* tmp = reinterpret_cast<int16_t*>(sc.r2_state);  // scratch, reused later
-  for (int i = lane; i < T.n_spawn && i < 64; i += 32) tmp[i] = (int16_t)T.spawn_cell[i];
+  int n_spawn = T.n_spawn;
+  if (T.spawn_cond) {
+    n_spawn = 0;
+    for (int base = 0; base < T.n_spawn && base < 64; base += 32) {
+      const int i = base + lane;
+      const bool on = i < T.n_spawn && choice_present(T, T.spawn_cond[i * 2], (uint32_t)T.spawn_cond[i * 2 + 1], episode, k0, k1);
+      const unsigned m = __ballot_sync(MP_FULL, on);
+      if (on) tmp[n_spawn + __popc(m & ((1u << lane) - 1u))] = (int16_t)T.spawn_cell[i];
+      n_spawn += __popc(m);
+    }
+  } else {
+    for (int i = lane; i < T.n_spawn && i < 64; i += 32) tmp[i] = (int16_t)T.spawn_cell[i];
+  }
   __syncwarp();
   if (lane == 0) {
     for (int p = 0; p < T.P; ++p) {
       uint4 w = philox4x32_10(0u, (uint32_t)episode, (uint32_t)p, RS_AVATAR_RESET, k0, k1);
-      int r = p + (int)pick(w.x, (uint32_t)(T.n_spawn - p));
+      int r = p + (int)pick(w.x, (uint32_t)(n_spawn - p));
       int16_t t = tmp[p]; tmp[p] = tmp[r]; tmp[r] = t;
     }
   }
@@ -156,7 +177,7 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
   // hit sprites live one frame (policy A.8)
   if (env[ENV_BEAM] & 1) { uint4 z = make_uint4(0, 0, 0, 0); uint4* l = reinterpret_cast<uint4*>(grid + (size_t)T.zap_layer * T.cells_pad); for (int i = lane; i < T.cells_pad / 8; i += 32) l[i] = z; }
   if (env[ENV_BEAM] & 2) { uint4 z = make_uint4(0, 0, 0, 0); uint4* l = reinterpret_cast<uint4*>(grid + (size_t)T.brush_layer * T.cells_pad); for (int i = lane; i < T.cells_pad / 8; i += 32) l[i] = z; }
-  if (env[ENV_BEAM] & 4) for (int c = lane; c < T.cells; c += 32) if (T.res_of_cell[c] < 0) grid[(size_t)T.claim_layer * T.cells_pad + c] = 0;
+  if (env[ENV_BEAM] & 4) for (int c = lane; c < T.cells; c += 32) { const int rr = T.res_of_cell[c]; if (rr < 0 || (sc.r[RU_FLAGS][rr] & RF_ABSENT)) grid[(size_t)T.claim_layer * T.cells_pad + c] = 0; }
   __syncwarp();
   int beam_dirty = 0;
 
@@ -357,7 +378,8 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
         uint32_t* bm = pass == 0 ? sc.bm_zap : (pass == 1 ? sc.bm_brush : sc.bm_claim);
         const int layer = pass == 0 ? T.zap_layer : (pass == 1 ? T.brush_layer : T.claim_layer);
         const int sprite = pass == 0 ? T.zap_sprite : (pass == 1 ? T.brush_sprite[src] : T.claimbeam_sprite[src]);
-        const bool layer_free = pass != 2 || T.res_of_cell[cell] < 0;  // the damage indicator occupies the claim layer
+        const int rr_here = pass == 2 ? T.res_of_cell[cell] : -1;
+        const bool layer_free = rr_here < 0 || (sc.r[RU_FLAGS][rr_here] & RF_ABSENT);  // a resource's damage indicator occupies the claim layer
         if (layer_free) {
           const uint32_t bit = 1u << (cell & 31);
           const uint32_t old = atomicOr(&bm[cell >> 5], bit);

@@ -181,8 +181,9 @@ class Lab2d:
     nested['levelName'] = level.rsplit('/', 1)[-1]  # builder.locate_and_overwrite_level_directory prefixed the directory
     self.settings = nested
     self.actions = ActionSpace(nested)
-    # 'choice' prefabs are drawn with the env's seed, as the reference draws them with the env's random stream
-    self.blob = compiler.compile_settings(nested, _PseudoConfig(nested, self.actions), build_seed=self.env_seed)
+    # ('choice' prefabs are left to the engine: drawn per env and episode from the env's RNG key, as the reference
+    # draws them with the env's random stream at every env build)
+    self.blob = compiler.compile_settings(nested, _PseudoConfig(nested, self.actions))
     self.info = blob_lib.unpack(self.blob)
     meta = self.info['meta']
     self.num_players = int(meta[4])

@@ -20,10 +20,11 @@ PRECOMPILED = {
     'coop_mining': (6,),
 }
 
-# Substrates with build-time randomness: 'choice' prefabs drawn per env instance (prefab_utils.lua:63-65), or
-# a builder that draws from Python's `random` (coins.py:45-84,488: map size, coin colours). A compiled blob
-# fixes one draw (policy A.20), made with this seed.
-BUILD_SEEDS = {'territory__inside_out': 0, 'coins': 0}
+# Substrates whose CONFIG BUILDER draws from Python's `random` (coins.py:45-84,488: map size, coin colours): the
+# reference makes one draw per `build()` call; a compiled blob fixes one draw, made with this seed (policy A.20).
+# ('choice' prefabs -- territory__inside_out -- are NOT fixed at compile time: the engine draws them per env and per
+# episode, as the reference's prefab_utils.lua:63-65 does at every env build.)
+BUILD_SEEDS = {'coins': 0}
 
 
 def blob_path(name: str, num_players: int) -> str:

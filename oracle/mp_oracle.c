@@ -35,7 +35,7 @@
  * the same numbers in any schedule. Policy A.16: the reference's mt19937_64 stream is out of
  * reach; every draw is addressed by (seed, episode, frame, stream, index).
  * ---------------------------------------------------------------------------------------- */
-enum { RS_SCENE = 0, RS_AVATAR = 1, RS_OBJECT = 2, RS_AVATAR_RESET = 3, RS_OBJECT_RESET = 4 };
+enum { RS_SCENE = 0, RS_AVATAR = 1, RS_OBJECT = 2, RS_AVATAR_RESET = 3, RS_OBJECT_RESET = 4, RS_CHOICE = 5 };
 enum { SCENE_DRAW_DIRT = 0, SCENE_DRAW_EPISODE_END = 1 };
 
 static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
@@ -80,6 +80,7 @@ typedef struct {
   int disallow_zapping, no_zap_counter;              /* Zapper (timed zapping prevention) */
   int n_connected, connected[4];                     /* Avatar:connect (pieces that move / turn with it) */
   int health, rewarding_active, claimed_by, never_claimed, destroyed, frames_since_zapped; /* Resource */
+  int absent; /* a 'choice' prefab that was not drawn into this episode's map: the piece does not exist */
   int texture_obj, damage_obj;                       /* Resource:postStart */
   int paired_resource;                               /* RewardIndicator */
   int claim_cool;                                    /* ResourceClaimer */
@@ -128,6 +129,7 @@ typedef struct OrEnv {
   int dirt_count, clean_count, spawner_t, ending_t;
   int cleaned_flag[OR_MAX_PLAYERS], ate_flag[OR_MAX_PLAYERS];
   uint8_t hit_class[64]; /* 1 = directionHit*, 2 = claimBeam_* */
+  int n_choice; int* choice_n; int* obj_choice; /* 'choice' prefabs drawn per env and episode: options per group; per object (group or -1, ticket mask) */
 } OrEnv;
 
 static const int DX[4] = {0, 1, 0, -1}, DY[4] = {-1, 0, 1, 0}; /* N E S W (component_library.lua:38-43) */
@@ -783,7 +785,7 @@ static void grid_update(OrEnv* e) {
     if (avatar_comp) {
       for (int i = 0; i < e->P; ++i) run_updater(e, u, e->avatar_obj[e->order[i]]);
     } else {
-      for (int oi = 0; oi < e->n_obj; ++oi) if (find_comp(e, &e->obj[oi], u->comp_type)) run_updater(e, u, oi);
+      for (int oi = 0; oi < e->n_obj; ++oi) if (!e->obj[oi].absent && find_comp(e, &e->obj[oi], u->comp_type)) run_updater(e, u, oi);
     }
   }
   process_queue(e);
@@ -796,6 +798,7 @@ static void simulation_update(OrEnv* e) {
   for (int p = 0; p < e->P; ++p) { Obj* a = &e->obj[e->avatar_obj[p]]; a->partner_match = 0; a->partner_mismatch = 0; } /* PartnerTracker:preUpdate (coins/components.lua:303-306) */
   for (int oi = 0; oi < e->n_obj; ++oi) {
     Obj* o = &e->obj[oi];
+    if (o->absent) continue;
     const KindDef* k = kind_of(e, o);
     for (int i = 0; i < k->n_comps; ++i) {
       const CompDef* c = &e->comps[k->comp0 + i];
@@ -898,6 +901,11 @@ static void episode_start(OrEnv* e) {
     memset(o, 0, sizeof *o);
     o->kind = d[MPB_OBJ_KIND]; o->x = d[MPB_OBJ_X]; o->y = d[MPB_OBJ_Y]; o->orient = d[MPB_OBJ_ORIENT];
     o->state = d[MPB_OBJ_STATE]; o->prev_state = -1; o->layer = -1; o->state_frame = 0; o->movement_allowed = 1;
+    if (e->obj_choice && e->obj_choice[oi * 2] >= 0) { /* prefab_utils.lua:63-65: random:choice(prefab.list), once per group */
+      uint32_t w[4]; rng(e, RS_CHOICE, e->obj_choice[oi * 2], w);
+      const uint32_t ticket = pick(w[0], (uint32_t)e->choice_n[e->obj_choice[oi * 2]]);
+      if (!(((uint32_t)e->obj_choice[oi * 2 + 1] >> ticket) & 1u)) { o->absent = 1; o->destroyed = 1; continue; }
+    }
     if (!kind_of(e, o)->is_avatar) { /* Transform:start -> createPiece (component_library.lua:236-254) */
       o->layer = state_def(e, o, o->state)->layer;
       place(e, oi);
@@ -929,6 +937,7 @@ static void episode_start(OrEnv* e) {
   /* postStart on all objects. */
   for (int oi = 0; oi < e->n_obj; ++oi) {
     Obj* o = &e->obj[oi];
+    if (o->absent) continue;
     const KindDef* k = kind_of(e, o);
     for (int i = 0; i < k->n_comps; ++i) {
       const CompDef* c = &e->comps[k->comp0 + i];
@@ -1051,6 +1060,9 @@ OrEnv* oracle_create(const void* blob, size_t n, uint64_t seed) {
     if (e->comps[i].type == MPB_C_PAINTBRUSH && e->comps[i].ip[1] < 64) e->hit_class[e->comps[i].ip[1]] = 1;
     if (e->comps[i].type == MPB_C_RESOURCE_CLAIMER && e->comps[i].ip[4] < 64) e->hit_class[e->comps[i].ip[4]] = 2;
   }
+  { const MpbSection* cg = mpb_find(blob, n, "choice_groups"); const MpbSection* oc = mpb_find(blob, n, "obj_choice");
+    if (cg && oc) { e->n_choice = (int)(cg->nbytes / 4); e->choice_n = (int*)malloc(cg->nbytes); memcpy(e->choice_n, mpb_data(blob, cg), cg->nbytes);
+                    e->obj_choice = (int*)malloc(oc->nbytes); memcpy(e->obj_choice, mpb_data(blob, oc), oc->nbytes); } }
   build_updaters(e);
   e->key[0] = (uint32_t)seed; e->key[1] = (uint32_t)(seed >> 32);
   e->episode = -1; e->done = 1;
@@ -1060,7 +1072,7 @@ void oracle_destroy(OrEnv* e) {
   if (!e) return;
   free(e->states); free(e->kinds); free(e->comps); free(e->objdef); free(e->hits); free(e->action_table); free(e->sprite_map);
   free(e->scalar_obs); free(e->atlas); free(e->sprite_opaque); free(e->obj); free(e->grid); free(e->beam); free(e->q); free(e->qnext);
-  free(e->ev); free(e->updaters); free(e);
+  free(e->ev); free(e->updaters); free(e->choice_n); free(e->obj_choice); free(e);
 }
 /* Starts the next episode; returns StepType.FIRST (0). */
 int oracle_reset(OrEnv* e) { e->episode++; episode_start(e); return 0; }

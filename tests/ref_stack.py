@@ -14,7 +14,7 @@ from meltingpot_b200 import compiler, lab2d_env, shims, substrates
 
 SEED = 4242
 STEPS = 48
-SUBSTRATES = [(name, counts[0]) for name, counts in substrates.PRECOMPILED.items() if name != 'territory__inside_out']
+SUBSTRATES = [(name, counts[0]) for name, counts in substrates.PRECOMPILED.items()]
 
 
 class OracleBackend:

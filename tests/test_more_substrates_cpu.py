@@ -90,13 +90,18 @@ def test_commons_closed_walls_keep_the_orchard_closed(oracle):
 
 
 @pytest.mark.skipif(compiler.reference_root() is None, reason='needs the reference checkout')
-def test_choice_prefabs_need_a_build_seed_and_differ_between_seeds():
-  # prefab_utils.lua:63-65: 'choice' is drawn at build time; policy A.20 fixes one draw per blob.
-  with pytest.raises(NotImplementedError, match='build_seed'):
-    compiler.compile_substrate('territory__inside_out', ('default',) * 5)
+def test_choice_prefabs_are_left_to_the_engine_unless_a_build_seed_fixes_them():
+  # prefab_utils.lua:63-65: 'choice' is drawn with the env's random stream at every env build. Without a build seed the
+  # blob carries the options (conditional objects) and the engine draws per env and episode; with one, a single draw is
+  # baked into the blob (the older behaviour, still available for reproducing one fixed layout).
+  from meltingpot_b200 import blob as blob_lib, substrates
+  per_env = compiler.compile_substrate('territory__inside_out', ('default',) * 5)
+  sec = blob_lib.unpack(per_env)
+  assert 'choice_groups' in sec and 'tr_res_cond' in sec and (sec['obj_choice'][:, 0] >= 0).sum() > 100
+  assert per_env == substrates.load_blob('territory__inside_out', ('default',) * 5)  # the committed blob is this one
   a = compiler.compile_substrate('territory__inside_out', ('default',) * 5, build_seed=1)
   b = compiler.compile_substrate('territory__inside_out', ('default',) * 5, build_seed=2)
-  assert a != b
+  assert a != b and 'choice_groups' not in blob_lib.unpack(a)
   assert a == compiler.compile_substrate('territory__inside_out', ('default',) * 5, build_seed=1)
 
 

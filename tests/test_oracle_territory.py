@@ -181,3 +181,31 @@ def test_torus_wraps_movement_and_views(oracle, territory_blob):
   assert tuple(env.avatars()[0][:2]) == (3, 20)                     # territory__rooms.py:91 topology TORUS
   cells = env.rgb()[0].reshape(11, 8, 11, 8, 3).transpose(0, 2, 1, 3, 4).reshape(121, -1)
   assert (cells != 0).any(axis=1).all()                             # no OutOfBounds (all-black) cell in a torus view
+
+
+def test_inside_out_choice_prefabs_are_drawn_per_env_and_per_episode(territory_inside_out_blob, oracle):
+  # prefab_utils.lua:63-65: a 'choice' prefab is drawn with the env's random stream at every env build, so every env
+  # instance -- and, through the ResetWrapper, every episode -- has its own map: territory__inside_out's 'A' / 'B'
+  # cells are resources with odds 2:1 / 1:3, its 'Q' cells spawn points with odds 1:6 (territory__inside_out.py:72-86).
+  from meltingpot_b200 import blob as blob_lib
+  sec = blob_lib.unpack(territory_inside_out_blob)
+  cond = sec['tr_res_cond']
+  n_cond = int((cond[:, 0] >= 0).sum())
+  assert n_cond > 50 and len(sec['choice_groups']) >= n_cond and 'spawn_cond_' + str(0) in sec or any(k.startswith('spawn_cond_') for k in sec)
+  counts, layouts = [], []
+  for seed in range(12):
+    e = oracle.OracleEnv(territory_inside_out_blob, 100 + seed)
+    e.reset()
+    g = e.grid()
+    res_layer = int(sec['tr_ip'][1])
+    layouts.append(g[res_layer].copy())
+    unclaimed = g[res_layer][0 * 0 + sec['tr_res'][:, 1]] == g[res_layer][int(sec['tr_res'][np.argmax(cond[:, 0] < 0), 1])]
+    counts.append(int(unclaimed.sum()))  # resource cells that show the 'unclaimed' resource sprite
+    if seed == 0:
+      e.reset()
+      assert not np.array_equal(e.grid()[res_layer][sec['tr_res'][:, 1]] != 0, layouts[0][sec['tr_res'][:, 1]] != 0)  # next episode: another draw
+  assert len({c for c in counts}) > 3               # envs differ
+  n_always = int((cond[:, 0] < 0).sum())
+  mean = np.mean(counts)
+  # expectation: always-present resources + 2/3 of the A cells + 1/4 of the B cells; a loose band around it
+  assert n_always + 0.2 * n_cond < mean < n_always + 0.7 * n_cond

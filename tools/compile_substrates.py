@@ -7,6 +7,7 @@ substrate configs; no reference source is copied.
   python tools/compile_substrates.py [name[:num_players] ...]
 """
 import os
+os.environ.setdefault('MELTINGPOT_REFERENCE_ROOT', '/root/reference')  # this tool runs where the checkout is
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
