@@ -225,3 +225,24 @@ def test_config5_sweep_at_2048_envs(name, players, oracle):
   blob = substrates.load_blob(name, ('default',) * players)
   stats = parity.compare_batch(blob, oracle, num_envs=2048, steps=30, seed=71, pixels_every=6)
   assert stats['pixel_checks'] == 6
+
+
+def test_inside_out_envs_of_one_batch_have_their_own_layouts(territory_inside_out_blob):
+  # Deviation A.20 is gone for 'choice' prefabs: every env (and episode) draws its own resources / spawn points.
+  import torch
+  from meltingpot_b200 import blob as blob_lib, engine
+  sec = blob_lib.unpack(territory_inside_out_blob)
+  cells = torch.as_tensor(sec['tr_res'][:, 1].astype(np.int64), device='cuda')
+  res_layer = int(sec['tr_ip'][1])
+  eng = engine.Engine(territory_inside_out_blob, 256, seed=3)
+  eng.reset()
+  torch.cuda.synchronize()
+  present = eng.grid[:, res_layer][:, cells] != 0
+  assert len({tuple(row.tolist()) for row in present.cpu()}) > 250          # (almost) every env its own layout
+  first = present.clone()
+  eng.reset()
+  torch.cuda.synchronize()
+  assert not torch.equal(eng.grid[:, res_layer][:, cells] != 0, first)      # and a new one every episode
+  frac = float(first.float().mean())
+  cond = sec['tr_res_cond']
+  assert (cond[:, 0] < 0).mean() < frac < 1.0
