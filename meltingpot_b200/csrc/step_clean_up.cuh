@@ -12,6 +12,8 @@
 
 #include "common.cuh"
 
+__host__ __device__ inline size_t scratch_round16(size_t n) { return (n + 15) & ~(size_t)15; }
+
 struct WarpScratch {  // per-warp shared memory, carved from the dynamic allocation
   uint8_t* occ;       // [cells_pad] 0 free, 1..P avatar p-1, 255 static piece on the avatar layer
   uint8_t* apple;     // [nA_pad] bit0 live this frame, bit1 eaten this frame
@@ -19,22 +21,31 @@ struct WarpScratch {  // per-warp shared memory, carved from the dynamic allocat
   uint32_t* beam_zap; // [cells/32+1] cells that already carry a zap sprite
   uint32_t* beam_2;   // same for the second beam
   int16_t* tmp;       // [64]
+  // per-CTA copies of static lookup tables (clean_up family): they sit on the serial avatar-by-avatar chain, where a
+  // shared-memory read costs ~30 cycles and an L2 round trip ~600
+  const int16_t* apple_of;  // [cells_pad] apple index or -1
+  const int16_t* dirt_of;   // [cells_pad] dirt index or -1
+  const uint8_t* flags;     // [cells_pad] BeamBlocker bits
+  const uint8_t* solid;     // [cells_pad] 255 where the avatar layer is statically occupied
+  const int32_t* act_table; // [n_actions][4]
 };
 
+__host__ __device__ inline size_t clean_up_table_bytes(const Tables& T) { return scratch_round16((size_t)T.cells_pad * 6) + scratch_round16((size_t)T.n_actions * 16); }
+
+// Every region starts 16-byte aligned (the per-entity state is moved with 128-bit accesses).
 __host__ __device__ inline size_t warp_scratch_bytes(const Tables& T) {
   size_t words = (size_t)(T.cells + 31) / 32 + 1;
-  size_t n = (size_t)T.cells_pad + T.nA_pad + T.nD_pad + 2 * words * 4 + 64 * 2;
-  return (n + 15) & ~(size_t)15;
+  return scratch_round16(T.cells_pad) + scratch_round16(T.nA_pad) + scratch_round16(T.nD_pad) + 2 * scratch_round16(words * 4) + 64 * 2;
 }
 
 __device__ __forceinline__ WarpScratch carve_scratch(const Tables& T, uint8_t* base) {
   WarpScratch s;
   size_t words = (size_t)(T.cells + 31) / 32 + 1;
-  s.occ = base; base += T.cells_pad;
-  s.apple = base; base += T.nA_pad;
-  s.dirt = base; base += T.nD_pad;
-  s.beam_zap = (uint32_t*)base; base += words * 4;
-  s.beam_2 = (uint32_t*)base; base += words * 4;
+  s.occ = base; base += scratch_round16(T.cells_pad);
+  s.apple = base; base += scratch_round16(T.nA_pad);
+  s.dirt = base; base += scratch_round16(T.nD_pad);
+  s.beam_zap = (uint32_t*)base; base += scratch_round16(words * 4);
+  s.beam_2 = (uint32_t*)base; base += scratch_round16(words * 4);
   s.tmp = (int16_t*)base;
   return s;
 }
@@ -140,16 +151,26 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
     x = a.x; y = a.y; orient = a.z; alive = a.w; zap_cool = t.x; clean_cool = t.y; state_frame = t.z;
     int id = actions[(size_t)b * T.P + lane];
     if (id < 0 || id >= T.n_actions) id = 0;
-    const int4 at = *reinterpret_cast<const int4*>(T.action_table + id * 4);  // discrete_action_wrapper.py:97-100
+    const int4 at = *reinterpret_cast<const int4*>(sc.act_table + id * 4);  // discrete_action_wrapper.py:97-100
     act_move = at.x; act_turn = at.y; act_zap = at.z; act_clean = at.w;
   }
   const int x0 = x, y0 = y, orient0 = orient, alive0 = alive;
   double reward = 0.0;  // Avatar:preUpdate (avatar_library.lua:330-332)
 
-  for (int i = lane; i < T.cells_pad / 4; i += 32)
-    reinterpret_cast<uint32_t*>(sc.occ)[i] = reinterpret_cast<const uint32_t*>(T.solid)[i];
-  for (int k = lane; k < T.nA; k += 32) sc.apple[k] = S.apple[(size_t)b * T.nA_pad + k];
-  for (int j = lane; j < T.nD; j += 32) sc.dirt[j] = S.dirt[(size_t)b * T.nD_pad + j];
+  for (int i = lane; i < T.cells_pad / 8; i += 32)
+    reinterpret_cast<uint2*>(sc.occ)[i] = reinterpret_cast<const uint2*>(sc.solid)[i];
+  // per-entity state, 16 entities per lane and access; bit 3 keeps the state the frame started with (round 2 compares
+  // against it instead of re-reading global memory)
+  for (int i = lane; i < T.nA_pad / 16; i += 32) {
+    uint4 v = reinterpret_cast<const uint4*>(S.apple + (size_t)b * T.nA_pad)[i];
+    v.x |= (v.x & 0x01010101u) << 3; v.y |= (v.y & 0x01010101u) << 3; v.z |= (v.z & 0x01010101u) << 3; v.w |= (v.w & 0x01010101u) << 3;
+    reinterpret_cast<uint4*>(sc.apple)[i] = v;
+  }
+  for (int i = lane; i < T.nD_pad / 16; i += 32) {
+    uint4 v = reinterpret_cast<const uint4*>(S.dirt + (size_t)b * T.nD_pad)[i];
+    v.x |= (v.x & 0x01010101u) << 3; v.y |= (v.y & 0x01010101u) << 3; v.z |= (v.z & 0x01010101u) << 3; v.w |= (v.w & 0x01010101u) << 3;
+    reinterpret_cast<uint4*>(sc.dirt)[i] = v;
+  }
   const int words = (T.cells + 31) / 32 + 1;
   for (int i = lane; i < words; i += 32) { sc.beam_zap[i] = 0; sc.beam_2[i] = 0; }
   __syncwarp();
@@ -261,10 +282,12 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
   for (int r = 0; r < T.P; ++r) {
     unsigned m = __ballot_sync(MP_FULL, is_av && rank == r);
     int src = __ffs(m) - 1;
-    int s_alive = __shfl_sync(MP_FULL, alive, src);
-    if (!s_alive) continue;
-    int s_turn = __shfl_sync(MP_FULL, act_turn, src), s_move = __shfl_sync(MP_FULL, act_move, src);
-    int sx = __shfl_sync(MP_FULL, x, src), sy = __shfl_sync(MP_FULL, y, src), so = __shfl_sync(MP_FULL, orient, src);
+    // one shuffle instead of six: alive | turn + 1 | move | orient | y | x
+    const uint32_t packed = __shfl_sync(MP_FULL, (uint32_t)(alive & 1) | ((uint32_t)(act_turn + 1) << 1) | ((uint32_t)act_move << 3) |
+                                                     ((uint32_t)orient << 6) | ((uint32_t)y << 8) | ((uint32_t)x << 20), src);
+    if (!(packed & 1u)) continue;
+    const int s_turn = (int)((packed >> 1) & 3u) - 1, s_move = (int)((packed >> 3) & 7u);
+    int so = (int)((packed >> 6) & 3u), sy = (int)((packed >> 8) & 0xfffu), sx = (int)(packed >> 20);
     if (s_turn != 0) so = (so + s_turn) & 3;
     bool ate = false;
     if (s_move != 0) {
@@ -278,7 +301,7 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
       }
       // place -> contact enter on the final cell, even when blocked (policy A.5)
       int fcell = sy * T.W + sx;
-      int ai = T.apple_of_cell[fcell];
+      int ai = sc.apple_of[fcell];
       ate = ai >= 0 && (sc.apple[ai] & 1);
       __syncwarp();
       if (ate && lane == 0) sc.apple[ai] |= 2;
@@ -306,12 +329,12 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
         else {
           cell = cy * T.W + cx;
           int hit = pass == 0 ? T.zap_hit : T.clean_hit;
-          if (T.cell_flags[cell] & (1 << hit)) blocked = true;  // BeamBlocker:onHit
+          if (sc.flags[cell] & (1 << hit)) blocked = true;  // BeamBlocker:onHit
           if (pass == 0) {
             int o = sc.occ[cell];
             if (o >= 1 && o <= T.P && o - 1 != src) { hit_avatar = o - 1; blocked = true; }  // Zapper:onHit
           } else {
-            int dj = T.dirt_of_cell[cell];
+            int dj = sc.dirt_of[cell];
             if (dj >= 0 && (sc.dirt[dj] & 1)) { hit_dirt = dj; blocked = true; }  // DirtCleaning:onHit
           }
         }
@@ -357,7 +380,7 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
     if (sc.occ[target] != 0) continue;  // blocked: the updater fires again next frame
     __syncwarp();
     if (lane == 0) sc.occ[target] = (uint8_t)(src + 1);
-    int ai = T.apple_of_cell[target];
+    int ai = sc.apple_of[target];
     bool ate = ai >= 0 && (sc.apple[ai] & 1);
     __syncwarp();
     if (ate && lane == 0) sc.apple[ai] |= 2;
@@ -373,7 +396,7 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
   if (is_av && (zapped >> lane & 1u)) { alive = 0; state_frame = n; }
   for (int k = lane; k < T.nA; k += 32) {
     uint8_t v = sc.apple[k];
-    uint8_t was = S.apple[(size_t)b * T.nA_pad + k];
+    uint8_t was = (v >> 3) & 1;
     uint8_t now = (v & 1) && !(v & 2);
     if (now != was) {
       S.apple[(size_t)b * T.nA_pad + k] = now;
@@ -383,7 +406,7 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
   int d_delta = 0;
   for (int j = lane; j < T.nD; j += 32) {
     uint8_t v = sc.dirt[j];
-    uint8_t was = S.dirt[(size_t)b * T.nD_pad + j];
+    uint8_t was = (v >> 3) & 1;
     uint8_t now = (v & 1) && !(v & 2);
     if ((v & 1) && (v & 2)) --d_delta;  // DirtTracker:onStateChange (clean_up/components.lua:118-129)
     if (now != was) {
@@ -395,8 +418,10 @@ __device__ void clean_up_step(const Tables& T, const State& S, int b, int lane, 
   dirt_count += d_delta;
   // water Animation (component_library.lua:1070-1094): every piece flips every anim_frames frames.
   if (n % T.anim_frames == 0) {
+    const int turn = (n / T.anim_frames) % T.n_anim;  // (uniform: the divisions are done once, not per piece)
     for (int k = lane; k < T.nW; k += 32) {
-      int phase = (S.water[(size_t)b * T.nW_pad + k] + n / T.anim_frames) % T.n_anim;
+      int phase = (int)S.water[(size_t)b * T.nW_pad + k] + turn;
+      if (phase >= T.n_anim) phase -= T.n_anim;
       grid[(size_t)T.water_layer * T.cells_pad + T.water[k * 2 + 1]] = cell_value(T.water_sprite[phase], 0);
     }
   }
@@ -441,10 +466,20 @@ __global__ void __launch_bounds__(128, 8) k_step_clean_up(Tables T, State S, con
   // Programmatic dependent launch, both ways: let the renderer that follows in the stream stage its tables while this
   // grid drains, and do not touch env state before the kernel that precedes this one (the previous render) is complete.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // static lookup tables into shared memory, once per CTA (before the dependency wait: they never change)
+  int16_t* s_apple_of = reinterpret_cast<int16_t*>(smem + 4 * warp_scratch_bytes(T));
+  int16_t* s_dirt_of = s_apple_of + T.cells_pad;
+  uint8_t* s_solid = reinterpret_cast<uint8_t*>(s_dirt_of + T.cells_pad);   // (8-byte aligned: cells_pad is a multiple of 8)
+  uint8_t* s_flags = s_solid + T.cells_pad;
+  int32_t* s_act = reinterpret_cast<int32_t*>(smem + 4 * warp_scratch_bytes(T) + scratch_round16((size_t)T.cells_pad * 6));
+  for (int i = threadIdx.x; i < T.cells_pad; i += (int)blockDim.x) { s_apple_of[i] = T.apple_of_cell[i]; s_dirt_of[i] = T.dirt_of_cell[i]; s_flags[i] = T.cell_flags[i]; s_solid[i] = T.solid[i]; }
+  for (int i = threadIdx.x; i < T.n_actions * 4; i += (int)blockDim.x) s_act[i] = T.action_table[i];
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  __syncthreads();
   const int b = blockIdx.x * 4 + warp;
   if (b >= S.B) return;
   WarpScratch sc = carve_scratch(T, smem + warp * warp_scratch_bytes(T));
+  sc.apple_of = s_apple_of; sc.dirt_of = s_dirt_of; sc.flags = s_flags; sc.solid = s_solid; sc.act_table = s_act;
   if (!(mode == 1 && !(mask == nullptr || mask[b]))) {
     event_begin(lane);
     if (mode == 1 || S.env[(size_t)b * ENV_COLS + ENV_DONE]) clean_up_reset(T, S, b, lane, sc);

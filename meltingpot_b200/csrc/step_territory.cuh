@@ -33,16 +33,21 @@ struct TerritoryScratch {
   uint8_t* r[RU_COUNT];    // resource bytes
   uint8_t* r2_state;       // state after the queued setStates (simulated in enqueue order)
   uint8_t* r2_changed;
+  uint8_t* was[4];         // state / reward indicator / damage indicator / texture as the frame started (round 2 writes the grid on change)
   uint16_t* fsz;
   uint16_t* frame;
   uint32_t* bm_zap; uint32_t* bm_brush; uint32_t* bm_claim;  // cells already carrying a hit sprite
   int* cnt;                // [MP_MAX_PLAYERS] rewards provided this frame per avatar
 };
 
+__host__ __device__ inline size_t tr_round16(size_t n) { return (n + 15) & ~(size_t)15; }
+
+// Layout: [fsz | frame] (as in fam_u16) then [r[0..RU_COUNT)] (as in fam_u8), both 16-byte aligned and contiguous so that
+// a frame moves them between HBM and shared memory with 128-bit accesses; then r2_state, r2_changed, the four
+// frame-start copies round 2 compares against, occ, the hit-sprite bitmaps and the reward counters.
 __host__ __device__ inline size_t territory_scratch_bytes(const Tables& T) {
   size_t words = (size_t)(T.cells + 31) / 32 + 1;
-  size_t n = (size_t)T.cells_pad + (RU_COUNT + 2) * (size_t)T.nR_pad + 2 * 2 * (size_t)T.nR_pad + 3 * words * 4 + MP_MAX_PLAYERS * 4;
-  return (n + 15) & ~(size_t)15;
+  return 2 * 2 * (size_t)T.nR_pad + (RU_COUNT + 2 + 4) * (size_t)T.nR_pad + tr_round16(T.cells_pad) + 3 * tr_round16(words * 4) + MP_MAX_PLAYERS * 4;
 }
 
 __device__ __forceinline__ TerritoryScratch carve_territory(const Tables& T, uint8_t* base) {
@@ -50,14 +55,15 @@ __device__ __forceinline__ TerritoryScratch carve_territory(const Tables& T, uin
   size_t words = (size_t)(T.cells + 31) / 32 + 1;
   s.fsz = (uint16_t*)base; base += 2 * T.nR_pad;
   s.frame = (uint16_t*)base; base += 2 * T.nR_pad;
-  s.bm_zap = (uint32_t*)base; base += words * 4;
-  s.bm_brush = (uint32_t*)base; base += words * 4;
-  s.bm_claim = (uint32_t*)base; base += words * 4;
-  s.cnt = (int*)base; base += MP_MAX_PLAYERS * 4;
-  s.occ = base; base += T.cells_pad;
   for (int i = 0; i < RU_COUNT; ++i) { s.r[i] = base; base += T.nR_pad; }
   s.r2_state = base; base += T.nR_pad;
-  s.r2_changed = base;
+  s.r2_changed = base; base += T.nR_pad;
+  for (int i = 0; i < 4; ++i) { s.was[i] = base; base += T.nR_pad; }
+  s.occ = base; base += tr_round16(T.cells_pad);
+  s.bm_zap = (uint32_t*)base; base += tr_round16(words * 4);
+  s.bm_brush = (uint32_t*)base; base += tr_round16(words * 4);
+  s.bm_claim = (uint32_t*)base; base += tr_round16(words * 4);
+  s.cnt = (int*)base;
   return s;
 }
 
@@ -162,11 +168,22 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
   }
   const int x0 = x, y0 = y, orient0 = orient, alive0 = alive, mk_on0 = mk_on, shown0 = shown;
   double reward = 0.0;  // Avatar:preUpdate
-  for (int k = lane; k < T.nR; k += 32) {
-#pragma unroll
-    for (int i = 0; i < RU_COUNT; ++i) sc.r[i][k] = u8[i * T.nR_pad + k];
-    sc.fsz[k] = u16[RS_FSZ * T.nR_pad + k]; sc.frame[k] = u16[RS_FRAME * T.nR_pad + k];
-    sc.r2_state[k] = sc.r[RU_STATE][k]; sc.r2_changed[k] = 0;
+  {  // per-resource state, 16 resources per lane and access (fam_u8 / fam_u16 rows and the scratch have the same layout)
+    const uint4* src8 = reinterpret_cast<const uint4*>(u8);
+    uint4* dst8 = reinterpret_cast<uint4*>(sc.r[0]);
+    for (int i = lane; i < RU_COUNT * T.nR_pad / 16; i += 32) dst8[i] = src8[i];
+    const uint4* src16 = reinterpret_cast<const uint4*>(u16);
+    uint4* dst16 = reinterpret_cast<uint4*>(sc.fsz);
+    for (int i = lane; i < RS_COUNT * T.nR_pad / 8; i += 32) dst16[i] = src16[i];
+    __syncwarp();
+    for (int i = lane; i < T.nR_pad / 16; i += 32) {
+      const uint4 st = reinterpret_cast<const uint4*>(sc.r[RU_STATE])[i];
+      reinterpret_cast<uint4*>(sc.r2_state)[i] = st; reinterpret_cast<uint4*>(sc.was[0])[i] = st;
+      reinterpret_cast<uint4*>(sc.was[1])[i] = reinterpret_cast<const uint4*>(sc.r[RU_IND])[i];
+      reinterpret_cast<uint4*>(sc.was[2])[i] = reinterpret_cast<const uint4*>(sc.r[RU_DMG])[i];
+      reinterpret_cast<uint4*>(sc.was[3])[i] = reinterpret_cast<const uint4*>(sc.r[RU_TEX])[i];
+      reinterpret_cast<uint4*>(sc.r2_changed)[i] = make_uint4(0, 0, 0, 0);
+    }
   }
   for (int i = lane; i < T.cells_pad; i += 32) sc.occ[i] = T.wall[i] ? 255 : 0;
   for (int i = lane; i < words; i += 32) { sc.bm_zap[i] = 0; sc.bm_brush[i] = 0; sc.bm_claim[i] = 0; }
@@ -398,16 +415,21 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
     const int cell = T.tr_res[k * 3 + 1];
     const int st_new = sc.r2_state[k];
     if (sc.r2_changed[k]) sc.frame[k] = (uint16_t)n;
-    const uint8_t was_state = u8[RU_STATE * T.nR_pad + k], was_ind = u8[RU_IND * T.nR_pad + k];
-    const uint8_t was_dmg = u8[RU_DMG * T.nR_pad + k], was_tex = u8[RU_TEX * T.nR_pad + k];
+    const uint8_t was_state = sc.was[0][k], was_ind = sc.was[1][k], was_dmg = sc.was[2][k], was_tex = sc.was[3][k];
     sc.r[RU_STATE][k] = (uint8_t)st_new;
     if (st_new != was_state) grid[(size_t)T.res_layer * T.cells_pad + cell] = resource_sprite_value(T, st_new);
     if (sc.r[RU_IND][k] != was_ind) grid[(size_t)T.ind_layer * T.cells_pad + cell] = sc.r[RU_IND][k] ? cell_value(T.dry_sprite[sc.r[RU_IND][k] - 1], 0) : (uint16_t)0;
     if (sc.r[RU_DMG][k] != was_dmg) grid[(size_t)T.dmg_layer * T.cells_pad + cell] = sc.r[RU_DMG][k] ? cell_value(T.dmg_sprite, 0) : (uint16_t)0;
     if (sc.r[RU_TEX][k] != was_tex) grid[(size_t)T.tex_layer * T.cells_pad + cell] = sc.r[RU_TEX][k] ? (uint16_t)0 : cell_value(T.tex_sprite, 0);
-#pragma unroll
-    for (int i = 0; i < RU_COUNT; ++i) u8[i * T.nR_pad + k] = sc.r[i][k];
-    u16[RS_FSZ * T.nR_pad + k] = sc.fsz[k]; u16[RS_FRAME * T.nR_pad + k] = sc.frame[k];
+  }
+  __syncwarp();
+  {
+    uint4* dst8 = reinterpret_cast<uint4*>(u8);
+    const uint4* src8 = reinterpret_cast<const uint4*>(sc.r[0]);
+    for (int i = lane; i < RU_COUNT * T.nR_pad / 16; i += 32) dst8[i] = src8[i];
+    uint4* dst16 = reinterpret_cast<uint4*>(u16);
+    const uint4* src16 = reinterpret_cast<const uint4*>(sc.fsz);
+    for (int i = lane; i < RS_COUNT * T.nR_pad / 8; i += 32) dst16[i] = src16[i];
   }
   // avatars and their markings
   const bool av_changed = is_av && (x != x0 || y != y0 || orient != orient0 || alive != alive0);
