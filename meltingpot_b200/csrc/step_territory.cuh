@@ -315,6 +315,51 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
   // beams: pass 0 zap (140), pass 1 paintbrush (130), pass 2 claim (100)
   for (int pass = 0; pass < 3; ++pass) {
     const BeamGeom& G = pass == 0 ? T.zap_geom : (pass == 1 ? T.brush_geom : T.claim_geom);
+    if (pass == 1 && G.n == 1 && G.fwd[0] == 1 && G.lat[0] == 0) {
+      // Paintbrush (territory/components.lua:362-412): every living avatar fires a one-cell beam every frame. The nine
+      // beams are resolved together, one lane per avatar, with exactly the outcome of visiting them in this frame's
+      // order: per resource the LAST claimant in order becomes the claimer; every claimant whose colour the resource does
+      // not already show emits its event; the queued state is that of the last such claimant; the hit sprite of a
+      // cell is the FIRST painter's (the sprite layer already holds one for later painters).
+      int cell = -1, res = -1; bool cond = false;
+      if (is_av && alive) {
+        int cx = x + dir_dx(orient), cy = y + dir_dy(orient);
+        if (wrap_or_reject(T, cx, cy)) {
+          const int c = cy * T.W + cx, o = sc.occ[c];
+          if (o != 255) cell = c;                       // AllBeamBlocker: no sprite, no hit
+          if (o == 254) {
+            res = T.res_of_cell[c];
+            cond = sc.r[RU_STATE][res] != 2 + lane && !(sc.r[RU_FLAGS][res] & RF_DESTROYED);
+          }
+        }
+      }
+      int last_all = rank, last_cond = cond ? rank : -1, n_cond = cond ? 1 : 0, first_cell = rank;
+      for (int q = 0; q < T.P; ++q) {
+        const int q_res = __shfl_sync(MP_FULL, res, q), q_cell = __shfl_sync(MP_FULL, cell, q), q_rank = __shfl_sync(MP_FULL, rank, q);
+        const bool q_cond = __shfl_sync(MP_FULL, (int)cond, q) != 0;
+        if (q == lane) continue;
+        if (res >= 0 && q_res == res) {
+          last_all = max(last_all, q_rank);
+          if (q_cond) { last_cond = max(last_cond, q_rank); ++n_cond; }
+        }
+        if (cell >= 0 && q_cell == cell) first_cell = min(first_cell, q_rank);
+      }
+      if (res >= 0) {
+        if (last_all == rank) sc.r[RU_CLAIMER][res] = (uint8_t)lane;
+        if (cond) emit_event(S, b, EV_CLAIMED_RESOURCE, lane + 1, 0);
+        if (cond && last_cond == rank) {
+          if (n_cond > 1 || sc.r2_state[res] != 2 + lane) { sc.r2_state[res] = (uint8_t)(2 + lane); sc.r2_changed[res] = 1; }
+          sc.r[RU_FLAGS][res] &= ~(RF_ACTIVE | RF_NEVER_CLAIMED);
+        }
+      }
+      if (cell >= 0 && first_cell == rank) {
+        atomicOr(&sc.bm_brush[cell >> 5], 1u << (cell & 31));
+        grid[(size_t)T.brush_layer * T.cells_pad + cell] = cell_value(T.brush_sprite[lane], orient);
+        beam_dirty |= 2;
+      }
+      __syncwarp();
+      continue;
+    }
     for (int r = 0; r < T.P; ++r) {
       const bool fires = pass == 0 ? fire_zap : (pass == 1 ? true : fire_claim);
       unsigned m = __ballot_sync(MP_FULL, is_av && rank == r && fires && alive);  // off-grid shooters: hitBeam is a no-op
