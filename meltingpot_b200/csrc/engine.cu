@@ -769,7 +769,7 @@ int launch_state(mp_engine* E, const int32_t* actions, const uint8_t* mask, int 
       E->family == MPB_FAMILY_CLEAN_UP ? k_step_clean_up : E->family == MPB_FAMILY_COMMONS_HARVEST ? k_step_commons :
       E->family == MPB_FAMILY_COINS ? k_step_coins : E->family == MPB_FAMILY_COOP_MINING ? k_step_mining : k_step_territory;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = E->step_smem * 4 + (E->family == MPB_FAMILY_CLEAN_UP ? clean_up_table_bytes(E->T) : 0); cfg.stream = st;
+  cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = E->step_smem * 4 + (E->family == MPB_FAMILY_CLEAN_UP ? clean_up_table_bytes(E->T) : E->family == MPB_FAMILY_TERRITORY ? territory_table_bytes(E->T) : 0); cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -954,7 +954,7 @@ int mp_create(const void* blob, size_t blob_bytes, int num_envs, int device, uin
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(E->render_gather_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kRenderSmemLimit);
   {
     static int step_smem_max[MP_MAX_DEVICES] = {};
-    const int need = (int)(E->step_smem * 4 + (E->family == MPB_FAMILY_CLEAN_UP ? clean_up_table_bytes(T) : 0));
+    const int need = (int)(E->step_smem * 4 + (E->family == MPB_FAMILY_CLEAN_UP ? clean_up_table_bytes(T) : E->family == MPB_FAMILY_TERRITORY ? territory_table_bytes(T) : 0));
     if (ce == cudaSuccess && need > 48 * 1024 && need > step_smem_max[device]) {
       ce = cudaFuncSetAttribute(k_step_clean_up, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
       if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k_step_commons, cudaFuncAttributeMaxDynamicSharedMemorySize, need);

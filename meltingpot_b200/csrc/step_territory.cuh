@@ -38,7 +38,17 @@ struct TerritoryScratch {
   uint16_t* frame;
   uint32_t* bm_zap; uint32_t* bm_brush; uint32_t* bm_claim;  // cells already carrying a hit sprite
   int* cnt;                // [MP_MAX_PLAYERS] rewards provided this frame per avatar
+  // per-CTA copies of static tables that sit on the frame's serial chain (an L2 round trip each otherwise)
+  const uint8_t* wall255;  // [cells_pad] 255 where an AllBeamBlocker stands, else 0 (the initial occupancy)
+  const int16_t* res_of;   // [cells_pad] resource index of a cell or -1
+  const int16_t* res_cell; // [nR_pad] cell of a resource
+  const int32_t* res_obj;  // [nR_pad] object id of a resource (RNG address)
 };
+
+__host__ __device__ inline size_t tr_round16(size_t n);
+__host__ __device__ inline size_t territory_table_bytes(const Tables& T) {
+  return ((size_t)T.cells_pad + 15) / 16 * 16 + ((size_t)T.cells_pad * 2 + 15) / 16 * 16 + (size_t)T.nR_pad * 2 + (size_t)T.nR_pad * 4;
+}
 
 __host__ __device__ inline size_t tr_round16(size_t n) { return (n + 15) & ~(size_t)15; }
 
@@ -185,16 +195,16 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
       reinterpret_cast<uint4*>(sc.r2_changed)[i] = make_uint4(0, 0, 0, 0);
     }
   }
-  for (int i = lane; i < T.cells_pad; i += 32) sc.occ[i] = T.wall[i] ? 255 : 0;
+  for (int i = lane; i < T.cells_pad / 8; i += 32) reinterpret_cast<uint2*>(sc.occ)[i] = reinterpret_cast<const uint2*>(sc.wall255)[i];
   for (int i = lane; i < words; i += 32) { sc.bm_zap[i] = 0; sc.bm_brush[i] = 0; sc.bm_claim[i] = 0; }
   if (lane < MP_MAX_PLAYERS) sc.cnt[lane] = 0;
   __syncwarp();
-  for (int k = lane; k < T.nR; k += 32) if (sc.r[RU_STATE][k] != 1) sc.occ[T.tr_res[k * 3 + 1]] = 254;  // resources stand on the avatar layer
+  for (int k = lane; k < T.nR; k += 32) if (sc.r[RU_STATE][k] != 1) sc.occ[sc.res_cell[k]] = 254;  // resources stand on the avatar layer
   if (is_av && alive) sc.occ[y * T.W + x] = (uint8_t)(lane + 1);
   // hit sprites live one frame (policy A.8)
   if (env[ENV_BEAM] & 1) { uint4 z = make_uint4(0, 0, 0, 0); uint4* l = reinterpret_cast<uint4*>(grid + (size_t)T.zap_layer * T.cells_pad); for (int i = lane; i < T.cells_pad / 8; i += 32) l[i] = z; }
   if (env[ENV_BEAM] & 2) { uint4 z = make_uint4(0, 0, 0, 0); uint4* l = reinterpret_cast<uint4*>(grid + (size_t)T.brush_layer * T.cells_pad); for (int i = lane; i < T.cells_pad / 8; i += 32) l[i] = z; }
-  if (env[ENV_BEAM] & 4) for (int c = lane; c < T.cells; c += 32) { const int rr = T.res_of_cell[c]; if (rr < 0 || (sc.r[RU_FLAGS][rr] & RF_ABSENT)) grid[(size_t)T.claim_layer * T.cells_pad + c] = 0; }
+  if (env[ENV_BEAM] & 4) for (int c = lane; c < T.cells; c += 32) { const int rr = sc.res_of[c]; if (rr < 0 || (sc.r[RU_FLAGS][rr] & RF_ABSENT)) grid[(size_t)T.claim_layer * T.cells_pad + c] = 0; }
   __syncwarp();
   int beam_dirty = 0;
 
@@ -219,7 +229,7 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
       int dmg = 1;
       int fsz = sc.fsz[k];
       if (fsz >= T.res_repair_delay) {
-        uint4 w = philox4x32_10((uint32_t)n, (uint32_t)episode, (uint32_t)T.tr_res[k * 3], RS_OBJECT, k0, k1);
+        uint4 w = philox4x32_10((uint32_t)n, (uint32_t)episode, (uint32_t)sc.res_obj[k], RS_OBJECT, k0, k1);
         if (u01(w.x, w.y) < T.res_repair_prob) { ++health; if (health == T.res_health0) dmg = 0; }
       }
       sc.r[RU_HEALTH][k] = (uint8_t)health;
@@ -260,7 +270,7 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
     const int age = n - (int)sc.frame[k];
     const int claimer = sc.r[RU_CLAIMER][k];
     if (age >= T.res_reward_delay) {
-      uint4 w = philox4x32_10((uint32_t)n, (uint32_t)episode, (uint32_t)T.tr_res[k * 3], RS_OBJECT, k0, k1);
+      uint4 w = philox4x32_10((uint32_t)n, (uint32_t)episode, (uint32_t)sc.res_obj[k], RS_OBJECT, k0, k1);
       if (u01(w.z, w.w) < T.res_rate && claimer != 0xFF) {
         if (alive_mask0 >> claimer & 1u) atomicAdd(&sc.cnt[claimer], 1);  // Avatar:addReward skips avatars in their wait state
         sc.r[RU_FLAGS][k] |= RF_ACTIVE;
@@ -328,7 +338,7 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
           const int c = cy * T.W + cx, o = sc.occ[c];
           if (o != 255) cell = c;                       // AllBeamBlocker: no sprite, no hit
           if (o == 254) {
-            res = T.res_of_cell[c];
+            res = sc.res_of[c];
             cond = sc.r[RU_STATE][res] != 2 + lane && !(sc.r[RU_FLAGS][res] & RF_DESTROYED);
           }
         }
@@ -377,7 +387,7 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
           const int o = sc.occ[cell];
           if (o == 255) blocked = true;  // AllBeamBlocker:onHit
           else if (o == 254) {
-            res = T.res_of_cell[cell];
+            res = sc.res_of[cell];
             if (pass == 0 && (int)sc.r[RU_HEALTH][res] - 1 != 0) blocked = true;  // zaps stop at an undestroyed resource
           } else if (o >= 1 && o <= T.P && o - 1 != src && pass == 0) { hit_avatar = o - 1; blocked = true; }  // Zapper:onHit
         }
@@ -440,7 +450,7 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
         uint32_t* bm = pass == 0 ? sc.bm_zap : (pass == 1 ? sc.bm_brush : sc.bm_claim);
         const int layer = pass == 0 ? T.zap_layer : (pass == 1 ? T.brush_layer : T.claim_layer);
         const int sprite = pass == 0 ? T.zap_sprite : (pass == 1 ? T.brush_sprite[src] : T.claimbeam_sprite[src]);
-        const int rr_here = pass == 2 ? T.res_of_cell[cell] : -1;
+        const int rr_here = pass == 2 ? sc.res_of[cell] : -1;
         const bool layer_free = rr_here < 0 || (sc.r[RU_FLAGS][rr_here] & RF_ABSENT);  // a resource's damage indicator occupies the claim layer
         if (layer_free) {
           const uint32_t bit = 1u << (cell & 31);
@@ -457,7 +467,7 @@ __device__ void territory_frame(const Tables& T, const State& S, int b, int lane
   // ---- round 2 + write back -----------------------------------------------------------------
   if (is_av && !alive && alive0) mk_on = 0;  // avatarStateChange('die') -> marking setState(waitState)
   for (int k = lane; k < T.nR; k += 32) {
-    const int cell = T.tr_res[k * 3 + 1];
+    const int cell = sc.res_cell[k];
     const int st_new = sc.r2_state[k];
     if (sc.r2_changed[k]) sc.frame[k] = (uint16_t)n;
     const uint8_t was_state = sc.was[0][k], was_ind = sc.was[1][k], was_dmg = sc.was[2][k], was_tex = sc.was[3][k];
@@ -514,10 +524,20 @@ __global__ void __launch_bounds__(128, 8) k_step_territory(Tables T, State S, co
   // Programmatic dependent launch, both ways: let the renderer that follows in the stream stage its tables while this
   // grid drains, and do not touch env state before the kernel that precedes this one (the previous render) is complete.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // static tables into shared memory, once per CTA (before the dependency wait: they never change)
+  uint8_t* tb = smem + 4 * territory_scratch_bytes(T);
+  uint8_t* s_wall = tb; tb += ((size_t)T.cells_pad + 15) / 16 * 16;
+  int16_t* s_res_of = reinterpret_cast<int16_t*>(tb); tb += ((size_t)T.cells_pad * 2 + 15) / 16 * 16;
+  int16_t* s_res_cell = reinterpret_cast<int16_t*>(tb); tb += (size_t)T.nR_pad * 2;
+  int32_t* s_res_obj = reinterpret_cast<int32_t*>(tb);
+  for (int i = threadIdx.x; i < T.cells_pad; i += (int)blockDim.x) { s_wall[i] = T.wall[i] ? 255 : 0; s_res_of[i] = T.res_of_cell[i]; }
+  for (int i = threadIdx.x; i < T.nR_pad; i += (int)blockDim.x) { s_res_cell[i] = i < T.nR ? (int16_t)T.tr_res[i * 3 + 1] : (int16_t)0; s_res_obj[i] = i < T.nR ? T.tr_res[i * 3] : 0; }
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  __syncthreads();
   const int b = blockIdx.x * 4 + warp;
   if (b >= S.B) return;
   TerritoryScratch sc = carve_territory(T, smem + warp * territory_scratch_bytes(T));
+  sc.wall255 = s_wall; sc.res_of = s_res_of; sc.res_cell = s_res_cell; sc.res_obj = s_res_obj;
   int32_t* env = S.env + (size_t)b * ENV_COLS;
   const uint64_t key = S.seed + (uint64_t)b;
   const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
