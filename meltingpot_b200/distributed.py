@@ -1,12 +1,14 @@
-"""Env-instance data parallelism: shard envs over ranks, gather the stacked scalar timestep.
+"""Env-instance data parallelism: shard envs over ranks, return the stacked timestep / observations to every rank.
 
 Env instances never interact (each `dmlab2d.Lab2d` is an isolated world,
 `/root/reference/meltingpot/utils/substrates/builder.py:179-187`), so the hot path itself needs
 no collective: rank r simply steps envs [base, base + count). Env b's RNG key is
 `seed + b` with b the GLOBAL env index, so results do not depend on the number of ranks.
-The only exchange is returning one stacked tensor per scalar timestep field to every rank
-(an all-gather over NCCL/NVLink, or gloo in the CPU tests); stacking the RGB observations is
-optional because it is NVLink-bound.
+The only exchange is returning one stacked tensor per timestep field (and, optionally, the stacked observations) to
+every rank. On B200s this is done by the engine itself: `connect_exchange` / `connect_gather_obs` hand every rank's
+buffers to every rank once (CUDA IPC handles over torch.distributed) and from then on the kernels deliver with
+peer-memory stores over NVLink (include/mp_engine.h, mp_exchange_* / mp_gather_obs_*). The plain collectives below
+(`all_gather_stacked`, `gather_timestep_scalars`; NCCL or gloo) remain for host-side logic and the CPU tests.
 """
 
 from __future__ import annotations
@@ -110,6 +112,33 @@ class ShardedSubstrate:
 
   def step(self, local_actions):
     return self.local.step(local_actions)
+
+  # -- engine-level exchanges (peer-memory stores from the kernels; no collective per step) ---------------------------
+  def connect(self, observations: bool = False) -> None:
+    """Wires this rank's engine into the stacked-timestep exchange (and the stacked-observation gather)."""
+    connect_exchange(self.local.engine, self._group)
+    if observations:
+      connect_gather_obs(self.local.engine, self._group)
+    self._connected = True
+
+  def stacked_timestep(self):
+    """(reward [G, P], discount [G], step_type [G]) of ALL ranks' envs for the step just taken (G = global envs).
+
+    Collective: every rank calls it once per step. The rows were written into this rank's buffer by the other ranks'
+    kernels; this enqueues the publish-and-wait kernel on the current stream and returns views of the buffer
+    (valid until two steps later)."""
+    import torch  # pylint: disable=g-import-not-at-top
+    eng = self.local.engine
+    eng.exchange_wait()
+    rows = eng.gathered_timestep()
+    p = eng.num_players
+    return rows[:, :p], rows[:, p], rows[:, p + 1].to(torch.int64)
+
+  def stacked_observations(self):
+    """(RGB [G, P, h, w, 3], WORLD.RGB [G, H, W, 3]) of all ranks' envs (needs connect(observations=True))."""
+    eng = self.local.engine
+    eng.gather_obs_wait()
+    return eng.gathered_observations()
 
   def gather_scalars(self, timestep):
     return gather_timestep_scalars(timestep.reward, timestep.discount, timestep.step_type, self._group)
