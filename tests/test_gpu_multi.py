@@ -144,3 +144,34 @@ def test_gather_obs_two_gpus_one_process(clean_up_blob):
     a = torch.randint(0, 9, (2 * B, 7), generator=gen, dtype=torch.int32)
     for r, e in enumerate(ranks):
       e.step(a[r * B:(r + 1) * B].contiguous().cuda(r))
+
+
+def test_sharded_substrate_world_of_one_over_torch_distributed(clean_up_blob):
+  # distributed.ShardedSubstrate end to end in a one-rank process group: IPC export of the exchange blocks, connect,
+  # stacked timestep and stacked observations equal the local ones.
+  import os
+  import torch
+  import torch.distributed as dist
+  from meltingpot_b200 import distributed
+  created = False
+  if not dist.is_initialized():
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1'); os.environ.setdefault('MASTER_PORT', '29533')
+    dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device('cuda', 0))
+    created = True
+  try:
+    sh = distributed.ShardedSubstrate('clean_up', ('default',) * 7, global_num_envs=64, seed=4, device=0)
+    assert (sh.env_index_base, sh.local_num_envs) == (0, 64)
+    sh.connect(observations=True)
+    ts = sh.reset()
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    for _ in range(5):
+      reward, discount, step_type = sh.stacked_timestep()
+      rgb, world = sh.stacked_observations()
+      torch.cuda.synchronize()
+      assert torch.equal(reward, ts.reward) and torch.equal(discount, ts.discount) and torch.equal(step_type, ts.step_type)
+      assert torch.equal(rgb, ts.observation['RGB']) and torch.equal(world, ts.observation['WORLD.RGB'])
+      ts = sh.step(torch.randint(0, 9, (64, 7), generator=gen, device='cuda', dtype=torch.int32))
+    sh.close()
+  finally:
+    if created:
+      dist.destroy_process_group()
