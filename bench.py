@@ -122,11 +122,24 @@ class ClockSampler(threading.Thread):
 # NUMA: a rank's pinned host buffers must live on the node its GPU hangs off, or the device->host stream crosses the
 # socket interconnect (GPU0-3 -> node 0, GPU4-7 -> node 1 on the 8-GPU boxes).
 # ---------------------------------------------------------------------------------------------------------------------
+def gpu_selector(local_rank):
+  """What `nvidia-smi -i` should be given for CUDA device `local_rank`: its UUID when torch reports one (an index would
+  name the wrong GPU under CUDA_VISIBLE_DEVICES), else the index."""
+  try:
+    import torch
+    uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    if uuid and uuid != 'None':
+      return uuid if uuid.startswith('GPU-') else 'GPU-' + uuid
+  except Exception:  # pylint: disable=broad-except
+    pass
+  return str(local_rank)
+
+
 def bind_to_gpu_numa_node(local_rank):
   """Pins this process (CPU affinity + preferred memory node) to the NUMA node of GPU `local_rank`. Best effort."""
   info = {'node': None, 'cpus': None, 'mempolicy': False}
   try:
-    bus = subprocess.run(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i', str(local_rank)],
+    bus = subprocess.run(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i', gpu_selector(local_rank)],
                          capture_output=True, text=True, timeout=10).stdout.strip().lower()
     if bus.startswith('00000000:'):
       bus = bus[4:]  # sysfs uses a 4-digit PCI domain
@@ -450,10 +463,10 @@ def run_gather_obs(job, n_g, dist, world, rank):
 
 
 def run_b200(args, rank, world, local_rank):
-  numa = bind_to_gpu_numa_node(local_rank)
   import torch
   if not torch.cuda.is_available():
     raise SystemExit('bench.py: no CUDA device; the B200 engine has no CPU path')
+  numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation (first touch decides the node)
   torch.cuda.set_device(local_rank)
   dist = None
   if world > 1:
@@ -474,7 +487,7 @@ def run_b200(args, rank, world, local_rank):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
-  sampler = ClockSampler(local_rank) if rank == 0 else None
+  sampler = ClockSampler(gpu_selector(local_rank)) if rank == 0 else None
   per_job, elapsed_ms, launches, env_steps = [], 0.0, 0, 0
   shard = None
   e2e = e2e_scalars = gather = None
