@@ -76,3 +76,29 @@ def test_reference_import_leaves_no_stub_modules_behind():
   import meltingpot  # this repo's alias package, not a stub of the checkout
   assert 'meltingpot_b200' in (meltingpot.__doc__ or '') and hasattr(meltingpot, 'substrate')
   assert not [k for k in sys.modules if k.startswith('meltingpot.configs')]
+
+
+@needs_reference
+@pytest.mark.parametrize('name,players', ref_stack.SUBSTRATES)
+def test_reference_substrate_test_helper_accepts_the_stack(name, players):
+  # The reference's own conformance helper (meltingpot/testing/substrates.py:22-68, used by substrate_test.py:24-47 for
+  # every substrate): action / reward / discount / observation specs against an actual step, run on the reference's
+  # stack over this repo's dmlab2d module.
+  import importlib
+  with ref_stack.reference_stack_on_oracle():
+    helper = importlib.import_module('meltingpot.testing.substrates')
+    ref_substrate = importlib.import_module('meltingpot.substrate')
+    config = ref_substrate.get_config(name)
+    roles = (tuple(config.default_player_roles)[0],) * players
+    case = helper.SubstrateTestCase('assert_step_matches_specs')
+    env = ref_substrate.build(name, roles=roles)
+    try:
+      case.assert_step_matches_specs(env)
+      # substrate_test.py:41-47: the factory's per-player specs equal the env's
+      factory = ref_substrate.get_factory(name)
+      assert env.action_spec()[0] == factory.action_spec()
+      assert set(env.observation_spec()[0]) >= set(factory.timestep_spec().observation)
+      for key, spec in factory.timestep_spec().observation.items():
+        assert env.observation_spec()[0][key] == spec, key
+    finally:
+      env.close()
