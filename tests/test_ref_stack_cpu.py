@@ -102,3 +102,27 @@ def test_reference_substrate_test_helper_accepts_the_stack(name, players):
         assert env.observation_spec()[0][key] == spec, key
     finally:
       env.close()
+
+
+@pytest.mark.parametrize('name,players', [('clean_up', 7), ('territory__rooms', 9)])
+def test_boundary_module_compiles_builder_settings_and_refuses_to_run_without_a_gpu(name, players):
+  # No reference checkout needed: the flattened settings builder.py handed to dmlab2d.Lab2d are committed. lab2d_env
+  # un-flattens and compiles them; apart from the action table (full product at this boundary) the blob equals the
+  # committed one. Constructing the environment needs the engine: without a CUDA device it raises, there is no CPU path.
+  import torch
+  from meltingpot_b200 import blob as blob_lib, engine, substrates
+  with gzip.open(os.path.join(ROOT, 'tests', 'golden', f'ref_stack_settings_{name}.json.gz')) as f:
+    flat = json.loads(f.read().decode())
+  lab = lab2d_env.Lab2d('', flat)
+  got, want = blob_lib.unpack(lab.blob), blob_lib.unpack(substrates.load_blob(name, ('default',) * players))
+  for key in ('objects', 'states', 'kinds', 'comps', 'comps_f', 'init_grid', 'atlas', 'sprite_map', 'hits', 'av_table'):
+    assert np.array_equal(got[key], want[key]), key
+  assert got['action_table'].shape[0] == len(lab.actions.table) > want['action_table'].shape[0]
+  for row in want['action_table']:  # every action of the substrate's discrete set is in the full product, at its mixed-radix index
+    fields = dict(zip(['move', 'turn', 'fireZap', 'fireClean' if name == 'clean_up' else 'fireClaim'], (int(v) for v in row)))
+    idx = lab.actions.index([fields[k] for k in lab.actions.order])
+    assert np.array_equal(got['action_table'][idx], row)
+  assert lab.observation_names()[:2] == ['1.RGB', '1.REWARD'] and lab.observation_names()[-1] == 'WORLD.RGB'
+  if not torch.cuda.is_available():
+    with pytest.raises(engine.EngineError, match='no CPU path'):
+      lab2d_env.Environment(env=lab, observation_names=lab.observation_names(), seed=lab.env_seed)
