@@ -105,11 +105,45 @@ class Subject:
 
 
 @dataclasses.dataclass(frozen=True)
+class Lab2dObservables:
+  """Same fields as the reference's Lab2dObservables (wrappers/observables.py:32-45): the raw dmlab2d-level stream."""
+  action: Subject      # {"1.move": ..., "1.turn": ..., ...} per step
+  timestep: Subject    # dm_env.TimeStep with the flat {"1.RGB", "1.REWARD", ..., "WORLD.RGB"} observation dict
+  events: Subject
+
+
+@dataclasses.dataclass(frozen=True)
 class SubstrateObservables:
   """Same fields as the reference's SubstrateObservables (substrate.py:32-44)."""
   action: Subject
   timestep: Subject
   events: Subject
+  dmlab2d: Optional[Lab2dObservables] = None
+
+
+def flat_action(action: Sequence[int], action_set: Sequence[Mapping[str, int]]) -> Dict[str, np.ndarray]:
+  """What the wrapper stack would hand to dmlab2d for these discrete actions (discrete_action_wrapper.py:97-100,
+  multiplayer_wrapper.py:120-130): {"<player>.<field>": int32 scalar}."""
+  out = {}
+  for i, a in enumerate(action):
+    for key, value in action_set[int(a)].items():
+      out[f'{i + 1}.{key}'] = np.array(value, dtype=np.int32)
+  return out
+
+
+def flat_timestep(timestep: 'dm_env.TimeStep', individual: Sequence[str], global_names: Sequence[str]) -> 'dm_env.TimeStep':
+  """The dmlab2d-level view of a multiplayer TimeStep: flat observation dict with "{i}.REWARD" entries, reward None on
+  FIRST else 0.0, discount None on FIRST (the inverse of multiplayer_wrapper.py:80-118)."""
+  obs = {}
+  for i, (player, reward) in enumerate(zip(timestep.observation, timestep.reward)):
+    for name in individual:
+      obs[f'{i + 1}.{name}'] = player[name]
+    obs[f'{i + 1}.REWARD'] = np.float64(reward)
+  for name in global_names:
+    obs[name] = timestep.observation[0][name]
+  first = timestep.step_type == dm_env.StepType.FIRST
+  return dm_env.TimeStep(step_type=timestep.step_type, reward=None if first else 0.0,
+                         discount=None if first else timestep.discount, observation=obs)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -221,7 +255,8 @@ class Substrate(dm_env.Environment):
     self._individual = list(config.individual_observation_names)
     self._global = list(config.global_observation_names)
     self._action_subject, self._timestep_subject, self._events_subject = Subject(), Subject(), Subject()
-    self._observables = SubstrateObservables(action=self._action_subject, timestep=self._timestep_subject,
+    self._raw = Lab2dObservables(action=Subject(), timestep=Subject(), events=Subject())
+    self._observables = SubstrateObservables(dmlab2d=self._raw, action=self._action_subject, timestep=self._timestep_subject,
                                              events=self._events_subject)
     self._closed = False
     self._last_observation = None
@@ -266,9 +301,22 @@ class Substrate(dm_env.Environment):
                            observation=observations)
 
   # -- dm_env API -------------------------------------------------------------------------------
+  def _emit_raw(self, timestep, action=None) -> None:
+    """observables().dmlab2d: the dmlab2d-level stream the reference's innermost ObservablesWrapper emits
+    (observables_wrapper.py:43-58), built only while somebody is subscribed."""
+    raw = self._raw
+    if action is not None and raw.action._observers:  # pylint: disable=protected-access
+      raw.action.on_next(flat_action(action, self._config.action_set))
+    if raw.timestep._observers:  # pylint: disable=protected-access
+      raw.timestep.on_next(flat_timestep(timestep, self._individual, self._global))
+    if raw.events._observers:  # pylint: disable=protected-access
+      for event in self.events():
+        raw.events.on_next(event)
+
   def reset(self) -> dm_env.TimeStep:
     self._batched.engine.reset_host(self._host_buffers())
     timestep = self._to_timestep()
+    self._emit_raw(timestep)
     self._timestep_subject.on_next(timestep)
     for event in self.events():
       self._events_subject.on_next(event)
@@ -286,6 +334,7 @@ class Substrate(dm_env.Environment):
     self._host_actions[0] = self._torch.as_tensor(np.asarray(action, np.int32))
     self._batched.engine.step_host(self._host_actions, host)
     timestep = self._to_timestep()
+    self._emit_raw(timestep, action)
     self._timestep_subject.on_next(timestep)
     for event in self.events():
       self._events_subject.on_next(event)
@@ -327,10 +376,24 @@ class Substrate(dm_env.Environment):
   def observables(self) -> SubstrateObservables:
     return self._observables
 
+  # dmlab2d's key-value debugging interface (wrappers/base.py:66-80): the engine exposes no properties.
+  def list_property(self, key: str = ''):
+    del key
+    return []
+
+  def read_property(self, key: str):
+    raise KeyError(key)
+
+  def write_property(self, key: str, value: str):
+    del value
+    raise KeyError(key)
+
   def close(self) -> None:
     if not self._closed:
       self._closed = True
       self._batched.close()
+      for subject in (self._raw.action, self._raw.timestep, self._raw.events):
+        subject.on_completed()
       self._action_subject.on_completed()
       self._timestep_subject.on_completed()
       self._events_subject.on_completed()

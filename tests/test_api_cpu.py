@@ -114,3 +114,25 @@ def test_product_package_never_imports_the_oracle():
       if f.endswith(('.py', '.cu', '.cuh', '.h')):
         text = open(os.path.join(dirpath, f), errors='ignore').read()
         assert not bad.search(text), f
+
+
+def test_dmlab2d_level_views_invert_the_multiplayer_wrapper():
+  # observables().dmlab2d carries the raw stream (wrappers/observables.py:32-45). flat_action / flat_timestep build it from
+  # the multiplayer TimeStep: {"<i>.<name>"} keys, "<i>.REWARD", reward / discount None on FIRST (multiplayer_wrapper.py:80-130).
+  rgb = [np.full((2, 2, 3), i, np.uint8) for i in range(2)]
+  world = np.zeros((4, 4, 3), np.uint8)
+  obs = [{'RGB': rgb[i], 'READY_TO_SHOOT': np.float64(i), 'WORLD.RGB': world, 'COLLECTIVE_REWARD': np.float64(3.0)} for i in range(2)]
+  ts = dm_env.TimeStep(dm_env.StepType.MID, [np.float64(1.0), np.float64(2.0)], 1.0, obs)
+  flat = substrate.flat_timestep(ts, ['RGB', 'READY_TO_SHOOT'], ['WORLD.RGB'])
+  assert set(flat.observation) == {'1.RGB', '1.READY_TO_SHOOT', '1.REWARD', '2.RGB', '2.READY_TO_SHOOT', '2.REWARD', 'WORLD.RGB'}
+  assert flat.observation['2.RGB'] is rgb[1] and flat.observation['WORLD.RGB'] is world
+  assert flat.observation['1.REWARD'] == 1.0 and flat.observation['2.REWARD'] == 2.0 and flat.reward == 0.0 and flat.discount == 1.0
+  first = substrate.flat_timestep(dm_env.TimeStep(dm_env.StepType.FIRST, [0.0, 0.0], 0.0, obs), ['RGB'], [])
+  assert first.reward is None and first.discount is None and set(first.observation) == {'1.RGB', '1.REWARD', '2.RGB', '2.REWARD'}
+  action_set = ({'move': 0, 'turn': 0, 'fireZap': 0}, {'move': 1, 'turn': 0, 'fireZap': 0}, {'move': 0, 'turn': -1, 'fireZap': 1})
+  act = substrate.flat_action([2, 1], action_set)
+  assert {k: int(v) for k, v in act.items()} == {'1.move': 0, '1.turn': -1, '1.fireZap': 1, '2.move': 1, '2.turn': 0, '2.fireZap': 0}
+  assert all(v.dtype == np.int32 and v.shape == () for v in act.values())
+  fields = {f.name for f in __import__('dataclasses').fields(substrate.SubstrateObservables)}
+  assert fields == {'action', 'timestep', 'events', 'dmlab2d'}
+  assert all(hasattr(substrate.Substrate, m) for m in ('list_property', 'read_property', 'write_property'))

@@ -126,3 +126,37 @@ def test_boundary_module_compiles_builder_settings_and_refuses_to_run_without_a_
   if not torch.cuda.is_available():
     with pytest.raises(engine.EngineError, match='no CPU path'):
       lab2d_env.Environment(env=lab, observation_names=lab.observation_names(), seed=lab.env_seed)
+
+
+@needs_reference
+def test_flat_views_equal_the_reference_stacks_own_dmlab2d_stream():
+  # The reference's innermost ObservablesWrapper emits the raw action dicts and flat TimeSteps (observables_wrapper.py:43-58).
+  # meltingpot_b200.substrate.flat_action / flat_timestep (what this repo's Substrate emits on observables().dmlab2d) must
+  # rebuild exactly that stream from the multiplayer-level action and TimeStep.
+  import importlib
+  from meltingpot_b200 import substrate as b200_substrate
+  with ref_stack.reference_stack_on_oracle():
+    ref_substrate = importlib.import_module('meltingpot.substrate')
+    config = ref_substrate.get_config('clean_up')
+    env = ref_substrate.build('clean_up', roles=('default',) * 7)
+    raw_ts, raw_act = [], []
+    env.observables().dmlab2d.timestep.subscribe(raw_ts.append)
+    env.observables().dmlab2d.action.subscribe(raw_act.append)
+    individual, global_names = list(config.individual_observation_names), list(config.global_observation_names)
+    action_set = [dict(a) for a in compiler._plain(config.action_set)]  # pylint: disable=protected-access
+    try:
+      rng = np.random.default_rng(2)
+      ts = env.reset()
+      for t in range(12):
+        mine = b200_substrate.flat_timestep(ts, individual, global_names)
+        ref = raw_ts[-1]
+        assert mine.step_type == ref.step_type and mine.reward == ref.reward and mine.discount == ref.discount
+        assert set(mine.observation) <= set(ref.observation)          # (the raw env offers every observation; the wrappers select)
+        for key, value in mine.observation.items():
+          assert np.array_equal(value, ref.observation[key]), key
+        acts = [int(a) for a in rng.integers(0, len(action_set), 7)]
+        ts = env.step(acts)
+        mine_act = b200_substrate.flat_action(acts, action_set)
+        assert set(mine_act) == set(raw_act[-1]) and all(int(mine_act[k]) == int(raw_act[-1][k]) for k in mine_act)
+    finally:
+      env.close()
