@@ -296,6 +296,10 @@ class Engine:
       out['event_count'] = torch.empty((B,), dtype=torch.int32).pin_memory()
     return out
 
+  def make_host_actions(self):
+    """Pinned int32 [B, P] host tensor for the actions of mp_step_host / mp_step_host_async."""
+    return self._torch.zeros((self.num_envs, self.num_players), dtype=self._torch.int32).pin_memory()
+
   @staticmethod
   def _host_struct(outputs) -> MpHostOutputs:
     s = MpHostOutputs()

@@ -270,7 +270,7 @@ class Substrate(dm_env.Environment):
     if self._host is None:
       eng = self._batched.engine
       self._host = eng.make_host_outputs(rgb=True, world_rgb=self._batched._world_rgb, events=True)  # pylint: disable=protected-access
-      self._host_actions = self._torch.zeros((1, self._num_players), dtype=self._torch.int32).pin_memory()
+      self._host_actions = eng.make_host_actions()
       self._scalar_index = {name: k for k, name in enumerate(self._batched._scalar_names)}  # pylint: disable=protected-access
     return self._host
 

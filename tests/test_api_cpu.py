@@ -136,3 +136,113 @@ def test_dmlab2d_level_views_invert_the_multiplayer_wrapper():
   fields = {f.name for f in __import__('dataclasses').fields(substrate.SubstrateObservables)}
   assert fields == {'action', 'timestep', 'events', 'dmlab2d'}
   assert all(hasattr(substrate.Substrate, m) for m in ('list_property', 'read_property', 'write_property'))
+
+
+class _FakeEngine:
+  """Stands in for engine.Engine in the host-logic test below: fills the pinned-buffer dict the way mp_reset_host /
+  mp_step_host do, with values that depend on the step count (no kernels, no oracle: nothing is computed)."""
+
+  def __init__(self, P, n_scalar, rgb_hw, world_hw, max_events=8):
+    self.num_players, self.num_scalar_obs = P, n_scalar
+    self.shape = (P, n_scalar, rgb_hw, world_hw, max_events)
+    self.t = -1
+    self.closed = False
+
+  def make_host_outputs(self, rgb=True, world_rgb=True, events=False):
+    import torch
+    P, n, (h, w), (H, W), M = self.shape
+    block = torch.zeros((P + 2 + max(n, 1) * P,), dtype=torch.float64)
+    out = {'scalar_block': block, 'reward': block[:P].view(1, P), 'discount': block[P:P + 1], 'step_type': block[P + 1:P + 2].view(torch.int64),
+           'scalar_obs': block[P + 2:].view(max(n, 1), 1, P), 'rgb': torch.zeros((1, P, h, w, 3), dtype=torch.uint8),
+           'world_rgb': torch.zeros((1, H, W, 3), dtype=torch.uint8), 'events': torch.zeros((1, M, 3), dtype=torch.int32),
+           'event_count': torch.zeros((1,), dtype=torch.int32)}
+    return out
+
+  def make_host_actions(self):
+    import torch
+    return torch.zeros((1, self.num_players), dtype=torch.int32)
+
+  def _fill(self, host, first):
+    self.t += 1
+    host['step_type'][0] = 0 if first else 1
+    host['discount'][0] = 0.0 if first else 1.0
+    host['reward'][0] = 0.0 if first else float(self.t)
+    host['scalar_obs'][:] = 0.5
+    host['rgb'][:] = self.t % 251
+    host['world_rgb'][:] = (self.t + 1) % 251
+    host['event_count'][0] = 0 if first else 1
+    host['events'][0, 0, 0] = 1; host['events'][0, 0, 1] = 1; host['events'][0, 0, 2] = 2   # zap(source 1, target 2)
+
+  def reset_host(self, host):
+    self._fill(host, True)
+
+  def step_host(self, actions, host):
+    assert tuple(actions.shape) == (1, self.num_players)
+    self.last_actions = actions.clone()
+    self._fill(host, False)
+
+  def close(self):
+    self.closed = True
+
+
+def test_substrate_host_logic_on_a_fake_engine():
+  # Substrate (the dm_env view, B = 1): timestep assembly, fresh arrays per step, shared WORLD.RGB object, COLLECTIVE_REWARD,
+  # action validation, events, all three observable levels incl. observables().dmlab2d, close().
+  config = substrate.get_config('clean_up')
+  env = substrate.Substrate.__new__(substrate.Substrate)
+  fake = _FakeEngine(7, 2, (88, 88), (168, 240))
+
+  class _Batched:
+    engine = fake
+    num_players = 7
+    _world_rgb = True
+    _scalar_names = ['READY_TO_SHOOT', 'NUM_OTHERS_WHO_CLEANED_THIS_STEP']
+
+    def close(self):
+      fake.close()
+
+  import torch
+  env._torch = torch
+  env._config = config
+  env._batched = _Batched()
+  env._num_players = 7
+  env._individual = list(config.individual_observation_names)
+  env._global = list(config.global_observation_names)
+  env._action_subject, env._timestep_subject, env._events_subject = substrate.Subject(), substrate.Subject(), substrate.Subject()
+  env._raw = substrate.Lab2dObservables(action=substrate.Subject(), timestep=substrate.Subject(), events=substrate.Subject())
+  env._observables = substrate.SubstrateObservables(dmlab2d=env._raw, action=env._action_subject, timestep=env._timestep_subject, events=env._events_subject)
+  env._closed, env._last_observation, env._last_events, env._host = False, None, np.zeros((0, 3), np.int32), None
+  seen = {k: [] for k in ('action', 'timestep', 'events', 'raw_action', 'raw_timestep', 'raw_events')}
+  env.observables().action.subscribe(seen['action'].append)
+  env.observables().timestep.subscribe(seen['timestep'].append)
+  env.observables().events.subscribe(seen['events'].append)
+  env.observables().dmlab2d.action.subscribe(seen['raw_action'].append)
+  env.observables().dmlab2d.timestep.subscribe(seen['raw_timestep'].append)
+  env.observables().dmlab2d.events.subscribe(seen['raw_events'].append)
+  ts0 = env.reset()
+  assert ts0.step_type == dm_env.StepType.FIRST and ts0.discount == 0.0 and ts0.reward == [0.0] * 7
+  assert set(ts0.observation[0]) == {'RGB', 'READY_TO_SHOOT', 'NUM_OTHERS_WHO_CLEANED_THIS_STEP', 'WORLD.RGB', 'COLLECTIVE_REWARD'}
+  assert ts0.observation[0]['WORLD.RGB'] is ts0.observation[6]['WORLD.RGB'] and ts0.observation[3]['RGB'].shape == (88, 88, 3)
+  ts1 = env.step([0, 1, 2, 3, 4, 5, 6])
+  assert ts1.step_type == dm_env.StepType.MID and ts1.discount == 1.0 and ts1.reward == [1.0] * 7 and ts1.observation[0]['COLLECTIVE_REWARD'] == 7.0
+  assert fake.last_actions.tolist() == [[0, 1, 2, 3, 4, 5, 6]]
+  assert int(ts0.observation[0]['RGB'][0, 0, 0]) == 0 and int(ts1.observation[0]['RGB'][0, 0, 0]) == 1   # fresh arrays each step
+  assert env.events() == [('zap', [b'dict', b'source', np.array(1.0), b'target', np.array(2.0)])]
+  assert env.observation() is not None and len(env.observation()) == 7
+  with pytest.raises(ValueError):
+    env.step([0] * 6)
+  with pytest.raises(ValueError):
+    env.step([9] * 7)
+  assert env.list_property('') == []
+  with pytest.raises(KeyError):
+    env.read_property('x')
+  assert len(seen['action']) == 1 and len(seen['timestep']) == 2 and len(seen['events']) == 1
+  assert len(seen['raw_timestep']) == 2 and len(seen['raw_action']) == 1 and len(seen['raw_events']) == 1
+  raw = seen['raw_timestep'][1]
+  assert raw.reward == 0.0 and raw.discount == 1.0 and raw.observation['3.REWARD'] == 1.0 and '7.RGB' in raw.observation and 'WORLD.RGB' in raw.observation
+  assert seen['raw_timestep'][0].reward is None and seen['raw_timestep'][0].discount is None
+  assert int(seen['raw_action'][0]['2.move']) == config.action_set[1]['move']
+  done = []
+  env.observables().timestep.subscribe(on_completed=lambda: done.append(1))
+  env.close()
+  assert fake.closed and done == [1]
